@@ -1,0 +1,29 @@
+# Top-level build: liblsdsort.so (the product) + the oracle checkers.
+# `python -c "import __graft_entry__ as g; g.build()"` runs the same commands.
+NVCC    ?= nvcc
+GENCODE := -gencode arch=compute_100a,code=sm_100a
+NVFLAGS := -O3 -std=c++17 -lineinfo $(GENCODE) -Xcompiler -fPIC -Xcompiler -fvisibility=hidden --expt-relaxed-constexpr
+CSRC    := lsdradixsort_b200/csrc
+OBJDIR  := build/obj
+SRCS    := api.cu sort.cu histogram.cu scan.cu onesweep_r1.cu onesweep_r2.cu onesweep_r4.cu onesweep_r8.cu
+OBJS    := $(addprefix $(OBJDIR)/,$(SRCS:.cu=.o))
+LIB     := lsdradixsort_b200/liblsdsort.so
+
+.PHONY: all lib oracle clean
+all: lib oracle
+
+lib: $(LIB)
+
+$(OBJDIR)/%.o: $(CSRC)/%.cu $(wildcard $(CSRC)/*.cuh) $(wildcard $(CSRC)/*.h) include/lsdsort.h
+	@mkdir -p $(OBJDIR)
+	$(NVCC) $(NVFLAGS) -Xptxas -v -c $< -o $@ 2> $(OBJDIR)/$*.ptxas.log || (cat $(OBJDIR)/$*.ptxas.log; false)
+
+$(LIB): $(OBJS)
+	$(NVCC) $(GENCODE) -shared -o $@ $(OBJS)
+
+oracle:
+	$(MAKE) -C oracle oracle ref
+
+clean:
+	rm -rf build $(LIB)
+	$(MAKE) -C oracle clean

@@ -1,0 +1,150 @@
+/*
+ * lsdsort.h -- C ABI of liblsdsort (B200 / sm_100a LSD radix sort of uint32 keys).
+ *
+ * This is the drop-in boundary for the one hot path of emanuele-xyz/LSDRadixSort.
+ * The reference has no header or FFI layer; its boundary is the set of free functions
+ * in LSDRadixSort/LSDRadixSort.cu.  Every entry point below names the reference
+ * interface it replaces (file:line, relative to the reference's LSDRadixSort/ dir).
+ *
+ * Conventions (all entry points):
+ *   - extern "C", plain pointers and sizes, no C++ or torch types.
+ *   - return an int status (LSD_OK == 0); nothing aborts or prints
+ *     (replaces CUDA_CALL / MYASSERT crash-on-error, CudaUtils.h:7-8, Utils.h:6-15).
+ *   - device pointers unless the name says "host"; caller owns all memory;
+ *     no hidden allocation: scratch comes from the *_workspace_bytes queries
+ *     (replaces GetGPUPrefixSumBlockSumsCount sizing, LSDRadixSort.cu:265-276, and the
+ *     3*G*H histogram scratch sized at :919-929).
+ *   - asynchronous on the caller's stream (`lsd_stream_t` is a cudaStream_t / CUstream);
+ *     the reference used the legacy default stream plus two streams it created per call
+ *     (LSDRadixSort.cu:841-842).
+ *   - n is 64-bit (the reference uses `int count` everywhere); any n >= 0 works, including
+ *     0, 1 and non-multiples of the tile (the reference requires count % block == 0).
+ *   - r = radix bits per digit, one of 1, 2, 4, 8 (reference: r in {1,2,4,8}, GPU path
+ *     rejects r > 10 at :953).  block = CUDA threads per block with the reference's
+ *     meaning; 0 picks the tuned default.
+ */
+#ifndef LSDSORT_H
+#define LSDSORT_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define LSD_API __declspec(dllexport)
+#else
+#define LSD_API __attribute__((visibility("default")))
+#endif
+
+typedef struct CUstream_st *lsd_stream_t; /* == cudaStream_t */
+
+enum lsd_status {
+    LSD_OK = 0,
+    LSD_ERR_INVALID_VALUE = 1,       /* bad r / block / bit_group / NULL pointer with n > 0 */
+    LSD_ERR_WORKSPACE_TOO_SMALL = 2, /* ws_bytes < the matching *_workspace_bytes query */
+    LSD_ERR_CUDA = 3,                /* a CUDA call or launch failed; see lsd_last_cuda_error */
+    LSD_ERR_UNSUPPORTED = 4,         /* size beyond what this build addresses */
+    LSD_ERR_ALIGNMENT = 5            /* key pointers must be 16-byte aligned, workspace 256-byte */
+};
+
+#define LSD_VERSION 100 /* 0.1.0 */
+
+LSD_API int lsd_version(void);
+LSD_API const char *lsd_status_string(int status);
+/* cudaError_t value behind the most recent LSD_ERR_CUDA on the calling thread (0 if none). */
+LSD_API int lsd_last_cuda_error(void);
+/* Bind the calling thread to a device (one process per GPU: call once with LOCAL_RANK). */
+LSD_API int lsd_set_device(int device);
+/* Device facts the host side sizes grids with: sm_count, max opt-in shared memory per block. */
+LSD_API int lsd_device_info(int *sm_count, int *smem_optin_bytes, int *cc_major, int *cc_minor);
+
+/* ---------------------------------------------------------------------------------------
+ * build_histogram
+ * Replaces: BuildHistogramsKernel<<<G,B,H*4>>>(a, h, count, r, bit_group)
+ *           (LSDRadixSort.cu:660-702; launched at :770 and :850), CPU twin
+ *           BuildHistogramsCPU (:643-658).
+ * hist is [G][2^r] tile-major uint32, G = ceil(n / block); every cell is overwritten
+ * (like the kernel; no pre-zeroing needed).  block is the keys-per-histogram of the
+ * reference (its threads per block), any value in [1, 2^20].
+ * ------------------------------------------------------------------------------------- */
+LSD_API size_t lsd_build_histogram_bytes(uint64_t n, int r, int block);
+LSD_API int lsd_build_histogram(const uint32_t *keys, uint64_t n, int r, int bit_group, int block,
+                                uint32_t *hist, lsd_stream_t stream);
+
+/* Whole-array histograms of ALL digits in one read of the keys:
+ * hist is [32/r][2^r] uint64, overwritten.  No reference counterpart as a function: it is
+ * the column sum of build_histogram over all tiles for every bit group (what the reference
+ * recomputes per pass at :850), hoisted out of the pass loop. */
+LSD_API int lsd_digit_histograms(const uint32_t *keys, uint64_t n, int r, uint64_t *hist, lsd_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * prefix_sum
+ * Replaces: void GPUPrefixSum(uint32_t* d_a, int count, int threads_per_block,
+ *                             uint32_t* d_block_sums, cudaStream_t s)  (LSDRadixSort.cu:286-302)
+ *           + int GetGPUPrefixSumBlockSumsCount(int count, int tpb)    (:265-276)
+ *           CPU twin PrefixSum (:128-139).
+ * In place, EXCLUSIVE, uint32 wrap-around (mod 2^32).  Single pass, decoupled look-back.
+ * ------------------------------------------------------------------------------------- */
+LSD_API size_t lsd_prefix_sum_workspace_bytes(uint64_t n, int block);
+LSD_API int lsd_prefix_sum(uint32_t *a, uint64_t n, int block, void *ws, size_t ws_bytes, lsd_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * LSD sort
+ * Replaces: void GPULSDRadixSort(uint32_t* a, uint32_t* b, uint32_t* h, uint32_t* block_sums,
+ *                                uint32_t* d, int grid, int block, int block_sums_count,
+ *                                int count, int h_count, int r)       (LSDRadixSort.cu:839-910)
+ *           CPU twin LSDRadixSort (:62-69).
+ * keys  : n keys in, ascending keys out (the reference leaves its result in `a`, :1005).
+ * scratch: n keys of ping-pong space (the reference's `b`); contents undefined afterwards.
+ * 32/r passes, least significant digit first, each pass stable.  Passes whose digit is
+ * constant over the whole input are skipped (decided on the device; the call stays async).
+ * ------------------------------------------------------------------------------------- */
+typedef struct lsd_sort_options {
+    uint32_t struct_bytes;  /* sizeof(lsd_sort_options); 0-initialise the rest */
+    uint32_t portion_keys;  /* 0 = default; max keys per look-back portion (tests use small values) */
+    uint32_t disable_skip;  /* 1 = run every pass even if its digit is constant */
+    uint32_t variant;       /* 0 = default kernel shape; other values select tuning variants */
+} lsd_sort_options;
+
+LSD_API size_t lsd_sort_workspace_bytes(uint64_t n, int r, int block);
+LSD_API size_t lsd_sort_workspace_bytes_ex(uint64_t n, int r, int block, const lsd_sort_options *opt);
+LSD_API int lsd_sort(uint32_t *keys, uint32_t *scratch, uint64_t n, int r, int block, void *ws, size_t ws_bytes,
+                     lsd_stream_t stream);
+LSD_API int lsd_sort_ex(uint32_t *keys, uint32_t *scratch, uint64_t n, int r, int block, void *ws, size_t ws_bytes,
+                        const lsd_sort_options *opt, lsd_stream_t stream);
+
+/* Same as lsd_sort_ex, but brackets every kernel with CUDA events on `stream`, synchronises,
+ * and reports per-stage device times.  stage_ms[0] = digit histogram + plan, stage_ms[1+p] =
+ * pass p (0 if skipped), stage_ms[1+passes] = copy-back (0 if none).  Measurement aid for
+ * bench.py's roofline leg; replaces the cudaEvent pair at LSDRadixSort.cu:999-1008. */
+LSD_API int lsd_sort_timed(uint32_t *keys, uint32_t *scratch, uint64_t n, int r, int block, void *ws,
+                           size_t ws_bytes, const lsd_sort_options *opt, lsd_stream_t stream, float *stage_ms,
+                           int stage_cap, int *stages_written);
+
+/* After a sort on `stream` has been enqueued: synchronises the stream and reports which
+ * passes the device-side plan skipped (bit p set = pass p skipped) and how many kernels
+ * of this library the sort launched. */
+LSD_API int lsd_sort_read_plan(const void *ws, uint64_t n, int r, uint32_t *skipped_mask, int *launches,
+                               lsd_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Host-buffer entry (what TestGPULSDRadixSort does around the call, LSDRadixSort.cu:1001-1005:
+ * H2D copy, sort, D2H copy).  The context owns the device buffers so repeated calls do not
+ * allocate.  host_keys may be pageable or pinned; the call returns after the sorted keys are
+ * back in host_keys.
+ * ------------------------------------------------------------------------------------- */
+typedef struct lsd_host_ctx lsd_host_ctx;
+LSD_API int lsd_host_ctx_create(uint64_t max_n, int r, int block, lsd_host_ctx **out);
+LSD_API int lsd_host_ctx_destroy(lsd_host_ctx *ctx);
+LSD_API int lsd_sort_host(lsd_host_ctx *ctx, uint32_t *host_keys, uint64_t n);
+/* Pinned host memory helpers (replace MyCudaHostAlloc, CudaUtils.cpp:3-8). */
+LSD_API int lsd_host_alloc(void **ptr, size_t bytes);
+LSD_API int lsd_host_free(void *ptr);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LSDSORT_H */

@@ -1,0 +1,24 @@
+"""lsdradixsort_b200 -- B200-native (sm_100a) LSD radix sort of uint32 keys.
+
+A drop-in for the one hot path of emanuele-xyz/LSDRadixSort (build_histogram, exclusive
+prefix_sum, LSD sort with radix bits R and block size B).  All compute is hand-written CUDA in
+``csrc/`` behind the C ABI of ``include/lsdsort.h``; this package is the host-side mirror.
+"""
+from ._native import LsdError, LIB_PATH, build_library  # noqa: F401
+from .api import (  # noqa: F401
+    BuildHistograms,
+    GetGPUPrefixSumBlockSumsCount,
+    GPULSDRadixSort,
+    GPUPrefixSum,
+    HostSorter,
+    Sorter,
+    SortInfo,
+    build_histogram,
+    digit_histograms,
+    prefix_sum_,
+    set_device,
+    sort_,
+    sort_workspace_bytes,
+)
+
+__version__ = "0.1.0"

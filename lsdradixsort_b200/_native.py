@@ -1,0 +1,110 @@
+"""ctypes binding of liblsdsort.so (the C ABI in include/lsdsort.h).
+
+The shared library is built in-tree by ``__graft_entry__.build()`` / ``make lib``.  There is no
+fallback: if the library is missing, importing the binding raises, and every wrapper turns a
+non-zero status into :class:`LsdError`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from pathlib import Path
+
+PKG_DIR = Path(__file__).resolve().parent
+REPO_ROOT = PKG_DIR.parent
+LIB_PATH = PKG_DIR / "liblsdsort.so"
+
+LSD_OK = 0
+LSD_ERR_INVALID_VALUE = 1
+LSD_ERR_WORKSPACE_TOO_SMALL = 2
+LSD_ERR_CUDA = 3
+LSD_ERR_UNSUPPORTED = 4
+LSD_ERR_ALIGNMENT = 5
+
+
+class LsdError(RuntimeError):
+    def __init__(self, status: int, where: str, detail: str = ""):
+        self.status = status
+        super().__init__(f"{where}: lsd status {status} ({detail})")
+
+
+class SortOptions(C.Structure):
+    _fields_ = [
+        ("struct_bytes", C.c_uint32),
+        ("portion_keys", C.c_uint32),
+        ("disable_skip", C.c_uint32),
+        ("variant", C.c_uint32),
+    ]
+
+
+def build_library(verbose: bool = False) -> Path:
+    """Compile liblsdsort.so for sm_100a with the repo Makefile (nvcc cross-compiles without a GPU)."""
+    cmd = ["make", "-C", str(REPO_ROOT), f"-j{os.cpu_count() or 4}", "lib"]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("building liblsdsort.so failed:\n" + res.stdout[-4000:] + res.stderr[-4000:])
+    if verbose:
+        print(res.stdout[-2000:])
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Load the native library (once).  Raises if it has not been built: no CPU fallback exists."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise ImportError(
+            f"{LIB_PATH} is missing. Build it with `make lib` or "
+            "`python -c 'import __graft_entry__ as g; g.build()'`; lsdradixsort_b200 has no CPU fallback."
+        )
+    l = C.CDLL(str(LIB_PATH))
+    u32p, u64p, vp = C.POINTER(C.c_uint32), C.POINTER(C.c_uint64), C.c_void_p
+    sig = {
+        "lsd_version": (C.c_int, []),
+        "lsd_status_string": (C.c_char_p, [C.c_int]),
+        "lsd_last_cuda_error": (C.c_int, []),
+        "lsd_set_device": (C.c_int, [C.c_int]),
+        "lsd_device_info": (C.c_int, [C.POINTER(C.c_int)] * 4),
+        "lsd_build_histogram_bytes": (C.c_size_t, [C.c_uint64, C.c_int, C.c_int]),
+        "lsd_build_histogram": (C.c_int, [vp, C.c_uint64, C.c_int, C.c_int, C.c_int, vp, vp]),
+        "lsd_digit_histograms": (C.c_int, [vp, C.c_uint64, C.c_int, vp, vp]),
+        "lsd_prefix_sum_workspace_bytes": (C.c_size_t, [C.c_uint64, C.c_int]),
+        "lsd_prefix_sum": (C.c_int, [vp, C.c_uint64, C.c_int, vp, C.c_size_t, vp]),
+        "lsd_sort_workspace_bytes": (C.c_size_t, [C.c_uint64, C.c_int, C.c_int]),
+        "lsd_sort_workspace_bytes_ex": (C.c_size_t, [C.c_uint64, C.c_int, C.c_int, C.POINTER(SortOptions)]),
+        "lsd_sort": (C.c_int, [vp, vp, C.c_uint64, C.c_int, C.c_int, vp, C.c_size_t, vp]),
+        "lsd_sort_ex": (C.c_int, [vp, vp, C.c_uint64, C.c_int, C.c_int, vp, C.c_size_t, C.POINTER(SortOptions), vp]),
+        "lsd_sort_timed": (
+            C.c_int,
+            [vp, vp, C.c_uint64, C.c_int, C.c_int, vp, C.c_size_t, C.POINTER(SortOptions), vp,
+             C.POINTER(C.c_float), C.c_int, C.POINTER(C.c_int)],
+        ),
+        "lsd_sort_read_plan": (C.c_int, [vp, C.c_uint64, C.c_int, u32p, C.POINTER(C.c_int), vp]),
+        "lsd_host_ctx_create": (C.c_int, [C.c_uint64, C.c_int, C.c_int, C.POINTER(vp)]),
+        "lsd_host_ctx_destroy": (C.c_int, [vp]),
+        "lsd_sort_host": (C.c_int, [vp, vp, C.c_uint64]),
+        "lsd_host_alloc": (C.c_int, [C.POINTER(vp), C.c_size_t]),
+        "lsd_host_free": (C.c_int, [vp]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(l, name)  # AttributeError here == the library does not export the header's symbol
+        fn.restype = res
+        fn.argtypes = args
+    l._lsd_signatures = sig
+    _lib = l
+    return l
+
+
+def check(status: int, where: str) -> None:
+    if status == LSD_OK:
+        return
+    l = lib()
+    detail = l.lsd_status_string(status).decode()
+    if status == LSD_ERR_CUDA:
+        detail += f", cudaError={l.lsd_last_cuda_error()}"
+    raise LsdError(status, where, detail)

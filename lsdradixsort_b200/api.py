@@ -1,0 +1,229 @@
+"""Host-side mirror of the reference's three entry points, over the C ABI.
+
+torch is used for device memory and streams only; every compute call goes through
+``liblsdsort.so`` (include/lsdsort.h).  Names follow the reference
+(LSDRadixSort/LSDRadixSort.cu): ``GPULSDRadixSort`` (:839), ``GPUPrefixSum`` (:286),
+``GetGPUPrefixSumBlockSumsCount`` (:265), ``BuildHistograms`` (kernel at :660); the snake_case
+functions are the same calls with the scratch management done for the caller.
+
+Keys are 32-bit words: tensors may be ``torch.uint32`` or ``torch.int32`` (bit pattern is what is
+sorted, as unsigned, ascending -- the reference's order).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+
+from . import _native as N
+
+_KEY_DTYPES = (torch.int32, torch.uint32)
+
+
+def _stream_ptr(device: torch.device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _check_keys(t: torch.Tensor, what: str) -> None:
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise TypeError(f"{what} must be a CUDA tensor (this library has no CPU path)")
+    if t.dtype not in _KEY_DTYPES:
+        raise TypeError(f"{what} must be int32/uint32, got {t.dtype}")
+    if not t.is_contiguous() or t.dim() != 1:
+        raise ValueError(f"{what} must be a contiguous 1-D tensor")
+
+
+def _options(portion_keys: int = 0, disable_skip: bool = False, variant: int = 0) -> Optional[N.SortOptions]:
+    if not (portion_keys or disable_skip or variant):
+        return None
+    return N.SortOptions(C.sizeof(N.SortOptions), int(portion_keys), int(bool(disable_skip)), int(variant))
+
+
+def set_device(index: int) -> None:
+    """Bind this process/thread to a GPU in both torch and the native library (one process per GPU)."""
+    torch.cuda.set_device(index)
+    N.check(N.lib().lsd_set_device(int(index)), "lsd_set_device")
+
+
+# --------------------------------------------------------------------------------------------------
+# build_histogram
+# --------------------------------------------------------------------------------------------------
+def build_histogram(keys: torch.Tensor, r: int, bit_group: int, block: int,
+                    out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Per-tile histograms ``h[G][2^r]`` of digit ``bit_group`` (reference layout, .cu:660-702)."""
+    _check_keys(keys, "keys")
+    n = keys.numel()
+    nbytes = N.lib().lsd_build_histogram_bytes(n, r, block)
+    if nbytes == 0 and n > 0:
+        raise N.LsdError(N.LSD_ERR_INVALID_VALUE, "lsd_build_histogram_bytes", "invalid r/block")
+    g = (n + block - 1) // block if block > 0 else 0
+    if out is None:
+        out = torch.empty((g, 1 << r), dtype=torch.int32, device=keys.device)
+    N.check(
+        N.lib().lsd_build_histogram(keys.data_ptr(), n, r, bit_group, block, out.data_ptr(), _stream_ptr(keys.device)),
+        "lsd_build_histogram",
+    )
+    return out
+
+
+def BuildHistograms(a: torch.Tensor, h: torch.Tensor, count: int, r: int, bit_group: int, grid: int, block: int) -> None:
+    """Reference-shaped call: ``BuildHistogramsKernel<<<grid, block>>>(a, h, count, r, bit_group)``."""
+    if grid != (count + block - 1) // block:
+        raise ValueError("grid must be ceil(count / block), as in the reference (.cu:710)")
+    build_histogram(a[:count], r, bit_group, block, out=h)
+
+
+def digit_histograms(keys: torch.Tensor, r: int = 8) -> torch.Tensor:
+    """Whole-array histograms of every digit in one read: ``[32/r][2^r]`` int64."""
+    _check_keys(keys, "keys")
+    out = torch.empty((32 // r, 1 << r), dtype=torch.int64, device=keys.device)
+    N.check(
+        N.lib().lsd_digit_histograms(keys.data_ptr(), keys.numel(), r, out.data_ptr(), _stream_ptr(keys.device)),
+        "lsd_digit_histograms",
+    )
+    return out
+
+
+# --------------------------------------------------------------------------------------------------
+# prefix_sum
+# --------------------------------------------------------------------------------------------------
+def GetGPUPrefixSumBlockSumsCount(count: int, threads_per_block: int) -> int:
+    """Scratch size in uint32 words for :func:`GPUPrefixSum` (reference .cu:265-276 returns words too)."""
+    return (N.lib().lsd_prefix_sum_workspace_bytes(count, threads_per_block) + 3) // 4
+
+
+def GPUPrefixSum(d_a: torch.Tensor, count: int, threads_per_block: int, d_block_sums: torch.Tensor) -> None:
+    """In-place exclusive scan mod 2^32 of ``d_a[:count]`` (reference .cu:286-302)."""
+    _check_keys(d_a, "d_a")
+    if d_block_sums.data_ptr() % 256:
+        raise ValueError("d_block_sums must be 256-byte aligned")
+    N.check(
+        N.lib().lsd_prefix_sum(d_a.data_ptr(), count, threads_per_block, d_block_sums.data_ptr(),
+                               d_block_sums.numel() * d_block_sums.element_size(), _stream_ptr(d_a.device)),
+        "lsd_prefix_sum",
+    )
+
+
+def prefix_sum_(a: torch.Tensor, block: int = 256) -> torch.Tensor:
+    """In-place exclusive prefix sum (uint32 wrap-around); allocates its own scratch."""
+    _check_keys(a, "a")
+    words = GetGPUPrefixSumBlockSumsCount(a.numel(), block)
+    ws = torch.empty(max(words, 64), dtype=torch.int32, device=a.device)
+    GPUPrefixSum(a, a.numel(), block, ws)
+    return a
+
+
+# --------------------------------------------------------------------------------------------------
+# LSD sort
+# --------------------------------------------------------------------------------------------------
+def sort_workspace_bytes(n: int, r: int = 8, block: int = 0, **opts) -> int:
+    o = _options(**opts)
+    return N.lib().lsd_sort_workspace_bytes_ex(n, r, block, C.byref(o) if o else None)
+
+
+def GPULSDRadixSort(a: torch.Tensor, b: torch.Tensor, h: torch.Tensor, count: int, block: int, r: int, **opts) -> None:
+    """Reference-shaped call (.cu:839): sort ``a[:count]`` ascending using ``b`` as ping-pong space and
+    ``h`` as scratch; the result is left in ``a``.  ``grid``, ``h_count``, ``d``, ``block_sums`` and
+    ``block_sums_count`` of the reference are derived or unused and therefore not parameters here."""
+    _check_keys(a, "a")
+    _check_keys(b, "b")
+    if b.numel() < count:
+        raise ValueError("b must hold at least `count` keys")
+    o = _options(**opts)
+    N.check(
+        N.lib().lsd_sort_ex(a.data_ptr(), b.data_ptr(), count, r, block, h.data_ptr(),
+                            h.numel() * h.element_size(), C.byref(o) if o else None, _stream_ptr(a.device)),
+        "lsd_sort",
+    )
+
+
+@dataclass
+class SortInfo:
+    skipped_mask: int
+    launches: int
+
+
+class Sorter:
+    """Reusable scratch + workspace for repeated sorts of up to ``max_n`` keys on one device."""
+
+    def __init__(self, max_n: int, r: int = 8, block: int = 0, device: Optional[torch.device] = None, **opts):
+        self.max_n, self.r, self.block, self.opts = int(max_n), int(r), int(block), opts
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        nbytes = sort_workspace_bytes(self.max_n, r, block, **opts)
+        if nbytes == 0 and self.max_n > 0:
+            raise N.LsdError(N.LSD_ERR_INVALID_VALUE, "lsd_sort_workspace_bytes", "invalid r/block/variant or n too large")
+        self.scratch = torch.empty(max(self.max_n, 1), dtype=torch.int32, device=self.device)
+        self.workspace = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=self.device)
+
+    def sort_(self, keys: torch.Tensor) -> torch.Tensor:
+        n = keys.numel()
+        if n > self.max_n:
+            raise ValueError("keys larger than this Sorter's capacity")
+        GPULSDRadixSort(keys, self.scratch, self.workspace, n, self.block, self.r, **self.opts)
+        return keys
+
+    def sort_timed_(self, keys: torch.Tensor) -> list:
+        """Sort and return per-stage device milliseconds [hist+plan, pass0.., copy-back] (synchronises)."""
+        _check_keys(keys, "keys")
+        stages = 32 // self.r + 2
+        buf = (C.c_float * stages)()
+        written = C.c_int(0)
+        o = _options(**self.opts)
+        N.check(
+            N.lib().lsd_sort_timed(keys.data_ptr(), self.scratch.data_ptr(), keys.numel(), self.r, self.block,
+                                   self.workspace.data_ptr(), self.workspace.numel(), C.byref(o) if o else None,
+                                   _stream_ptr(keys.device), buf, stages, C.byref(written)),
+            "lsd_sort_timed",
+        )
+        return list(buf)[: written.value]
+
+    def info(self, n: int) -> SortInfo:
+        mask, launches = C.c_uint32(0), C.c_int(0)
+        N.check(
+            N.lib().lsd_sort_read_plan(self.workspace.data_ptr(), n, self.r, C.byref(mask), C.byref(launches),
+                                       _stream_ptr(self.device)),
+            "lsd_sort_read_plan",
+        )
+        return SortInfo(mask.value, launches.value)
+
+
+def sort_(keys: torch.Tensor, r: int = 8, block: int = 0, **opts) -> torch.Tensor:
+    """Sort ``keys`` in place, ascending as unsigned 32-bit; allocates scratch for this one call."""
+    _check_keys(keys, "keys")
+    return Sorter(keys.numel(), r, block, device=keys.device, **opts).sort_(keys)
+
+
+class HostSorter:
+    """Host-buffer entry: H2D copy, sort, D2H copy in one call (reference .cu:1001-1005)."""
+
+    def __init__(self, max_n: int, r: int = 8, block: int = 0):
+        self._ctx = C.c_void_p()
+        N.check(N.lib().lsd_host_ctx_create(int(max_n), r, block, C.byref(self._ctx)), "lsd_host_ctx_create")
+        self.max_n = int(max_n)
+
+    def sort_(self, host_keys) -> None:
+        """``host_keys``: pinned/pageable CPU torch tensor (int32/uint32) or numpy uint32 array, sorted in place."""
+        if isinstance(host_keys, torch.Tensor):
+            if host_keys.is_cuda or host_keys.dtype not in _KEY_DTYPES or not host_keys.is_contiguous():
+                raise TypeError("host_keys must be a contiguous CPU int32/uint32 tensor")
+            ptr, n = host_keys.data_ptr(), host_keys.numel()
+        else:
+            import numpy as np
+
+            if host_keys.dtype != np.uint32 or not host_keys.flags["C_CONTIGUOUS"]:
+                raise TypeError("host_keys must be a C-contiguous uint32 array")
+            ptr, n = host_keys.ctypes.data, host_keys.size
+        N.check(N.lib().lsd_sort_host(self._ctx, ptr, n), "lsd_sort_host")
+
+    def close(self) -> None:
+        if self._ctx:
+            N.lib().lsd_host_ctx_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,198 @@
+// histogram.cu -- the two histogram kernels of liblsdsort.
+//
+// (1) digit_hist_kernel: ONE read of the keys builds the whole-array histograms of all
+//     32/r digits (north_star step 1).  Replaces the per-pass BuildHistogramsKernel launch
+//     of the reference (LSDRadixSort.cu:850) on the sort path.
+// (2) tile_hist_kernel: the reference-layout [G][2^r] per-tile histogram of one digit,
+//     i.e. the drop-in for BuildHistogramsKernel (LSDRadixSort.cu:660-702).
+#include "common.cuh"
+
+namespace lsd {
+
+// -------------------------------------------------------------------------------------
+// (1) Whole-array digit histograms.
+//
+// Data layout in shared memory: cnt[row][lane], row = pass * H + digit, 32 uint32 per row.
+// A thread only ever touches column `lane`, so every shared atomic of a warp instruction
+// lands in 32 distinct banks whatever the key distribution is (uniform, all-equal, sorted):
+// no bank conflicts and no same-address serialisation inside a warp.  R=8 needs
+// 4*256*32*4 B = 128 KiB, which is why this kernel runs one 1024-thread CTA per SM
+// (B200: 227 KiB opt-in shared memory per CTA).  Keys are read with 128-bit streaming
+// loads, four in flight per thread.  The flush reads each row along a diagonal (column
+// (j + lane) & 31) so that it is conflict-free too, and issues one 64-bit global atomic
+// per non-empty (pass, digit).
+// Algorithmic bytes: 4 B per key read; the 32/r * 2^r * 8 B output is negligible.
+// -------------------------------------------------------------------------------------
+constexpr int kHistThreads = 1024;
+
+template <int RB>
+__device__ __forceinline__ void hist_add_key(uint32_t* cnt_lane, uint32_t key)
+{
+    constexpr int NP = 32 / RB;
+    constexpr int H = 1 << RB;
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+        const uint32_t d = (key >> (p * RB)) & (H - 1);
+        atomicAdd(cnt_lane + ((p * H + d) << 5), 1u);
+    }
+}
+
+template <int RB>
+__global__ void __launch_bounds__(kHistThreads, 1)
+digit_hist_kernel(const uint32_t* __restrict__ keys, uint64_t n, unsigned long long* __restrict__ hist)
+{
+    constexpr int NP = 32 / RB;
+    constexpr int H = 1 << RB;
+    constexpr int ROWS = NP * H;
+    extern __shared__ uint32_t cnt[];  // [ROWS][32]
+
+    const uint32_t tid = threadIdx.x;
+    const uint32_t lane = tid & 31u;
+    for (uint32_t i = tid; i < ROWS * 32; i += kHistThreads) cnt[i] = 0;
+    __syncthreads();
+
+    uint32_t* cnt_lane = cnt + lane;
+    const uint64_t nvec = n >> 2;
+    const uint64_t stride = (uint64_t)gridDim.x * kHistThreads;
+    uint64_t i = (uint64_t)blockIdx.x * kHistThreads + tid;
+
+    // main body: 4 independent 128-bit loads in flight per thread
+    for (; i + 3 * stride < nvec; i += 4 * stride) {
+        const uint4 a = ld_stream_v4(keys + 4 * i);
+        const uint4 b = ld_stream_v4(keys + 4 * (i + stride));
+        const uint4 c = ld_stream_v4(keys + 4 * (i + 2 * stride));
+        const uint4 d = ld_stream_v4(keys + 4 * (i + 3 * stride));
+        hist_add_key<RB>(cnt_lane, a.x); hist_add_key<RB>(cnt_lane, a.y);
+        hist_add_key<RB>(cnt_lane, a.z); hist_add_key<RB>(cnt_lane, a.w);
+        hist_add_key<RB>(cnt_lane, b.x); hist_add_key<RB>(cnt_lane, b.y);
+        hist_add_key<RB>(cnt_lane, b.z); hist_add_key<RB>(cnt_lane, b.w);
+        hist_add_key<RB>(cnt_lane, c.x); hist_add_key<RB>(cnt_lane, c.y);
+        hist_add_key<RB>(cnt_lane, c.z); hist_add_key<RB>(cnt_lane, c.w);
+        hist_add_key<RB>(cnt_lane, d.x); hist_add_key<RB>(cnt_lane, d.y);
+        hist_add_key<RB>(cnt_lane, d.z); hist_add_key<RB>(cnt_lane, d.w);
+    }
+    for (; i < nvec; i += stride) {
+        const uint4 a = ld_stream_v4(keys + 4 * i);
+        hist_add_key<RB>(cnt_lane, a.x); hist_add_key<RB>(cnt_lane, a.y);
+        hist_add_key<RB>(cnt_lane, a.z); hist_add_key<RB>(cnt_lane, a.w);
+    }
+    // ragged tail (n % 4 keys) -- block 0 only
+    if (blockIdx.x == 0) {
+        const uint64_t t = (nvec << 2) + tid;
+        if (t < n) hist_add_key<RB>(cnt_lane, keys[t]);
+    }
+    __syncthreads();
+
+    for (uint32_t row = tid; row < ROWS; row += kHistThreads) {
+        const uint32_t* r = cnt + (row << 5);
+        uint32_t sum = 0;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) sum += r[(j + lane) & 31];
+        if (sum) atomicAdd(hist + row, (unsigned long long)sum);
+    }
+}
+
+template <int RB>
+static int launch_digit_hist_t(const uint32_t* keys, uint64_t n, uint64_t* hist, cudaStream_t s)
+{
+    constexpr int ROWS = (32 / RB) << RB;
+    const size_t smem = (size_t)ROWS * 32 * sizeof(uint32_t);
+    LSD_CUDA_TRY(cudaMemsetAsync(hist, 0, (size_t)ROWS * sizeof(uint64_t), s));
+    if (n == 0) return LSD_OK;
+    LSD_CUDA_TRY(cudaFuncSetAttribute(digit_hist_kernel<RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // one CTA per SM, but never more CTAs than there are 16 KiB slices of input
+    const uint64_t slices = ((n >> 2) + kHistThreads - 1) / kHistThreads;
+    int grid = sm_count();
+    if ((uint64_t)grid > slices) grid = (int)(slices ? slices : 1);
+    digit_hist_kernel<RB><<<grid, kHistThreads, smem, s>>>(keys, n, reinterpret_cast<unsigned long long*>(hist));
+    LSD_LAUNCH_CHECK();
+    return LSD_OK;
+}
+
+int launch_digit_histograms(const uint32_t* keys, uint64_t n, int r, uint64_t* hist, cudaStream_t s)
+{
+    switch (r) {
+        case 1: return launch_digit_hist_t<1>(keys, n, hist, s);
+        case 2: return launch_digit_hist_t<2>(keys, n, hist, s);
+        case 4: return launch_digit_hist_t<4>(keys, n, hist, s);
+        case 8: return launch_digit_hist_t<8>(keys, n, hist, s);
+    }
+    return LSD_ERR_INVALID_VALUE;
+}
+
+// -------------------------------------------------------------------------------------
+// (2) Reference-layout per-tile histograms: h[g*H + d] = #{keys of tile g with digit d},
+//     tile g = keys [g*block, min((g+1)*block, n)).  One warp owns a tile at a time and
+//     walks tiles with a grid stride, so any `block` works (the reference ties it to the
+//     CUDA block size).  H <= 4 counts with ballots (no shared memory at all: two or four
+//     addresses would serialise 32 atomics); H >= 16 uses a warp-private shared histogram.
+//     Output rows are written coalesced.  Algorithmic bytes: 4 B/key read + G*H*4 B written.
+// -------------------------------------------------------------------------------------
+constexpr int kTileHistThreads = 256;
+
+template <int RB>
+__global__ void __launch_bounds__(kTileHistThreads)
+tile_hist_kernel(const uint32_t* __restrict__ keys, uint64_t n, int shift, uint32_t block, uint64_t tiles,
+                 uint32_t* __restrict__ hist)
+{
+    constexpr int H = 1 << RB;
+    constexpr int WARPS = kTileHistThreads / 32;
+    __shared__ uint32_t wh[WARPS][H >= 16 ? H : 1];
+
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t warp = threadIdx.x >> 5;
+    const uint64_t warp_stride = (uint64_t)gridDim.x * WARPS;
+
+    for (uint64_t g = (uint64_t)blockIdx.x * WARPS + warp; g < tiles; g += warp_stride) {
+        const uint64_t lo = g * block;
+        const uint64_t rem = n - lo;
+        const uint32_t len = rem < block ? (uint32_t)rem : block;
+        const uint32_t* src = keys + lo;
+        uint32_t* dst = hist + g * H;
+
+        if constexpr (H <= 4) {
+            uint32_t mine = 0;  // lane v (< H) accumulates the count of digit v
+            for (uint32_t base = 0; base < len; base += 32) {
+                const uint32_t i = base + lane;
+                const bool ok = i < len;
+                const uint32_t d = ok ? digit_of<RB>(src[i], shift) : 0u;
+#pragma unroll
+                for (int v = 0; v < H; ++v) {
+                    const uint32_t c = __popc(__ballot_sync(kFullMask, ok && d == (uint32_t)v));
+                    if (lane == (uint32_t)v) mine += c;
+                }
+            }
+            if (lane < H) dst[lane] = mine;
+        } else {
+            uint32_t* my = wh[warp];
+            for (uint32_t d = lane; d < H; d += 32) my[d] = 0;
+            __syncwarp();
+            for (uint32_t i = lane; i < len; i += 32) atomicAdd(&my[digit_of<RB>(src[i], shift)], 1u);
+            __syncwarp();
+            for (uint32_t d = lane; d < H; d += 32) dst[d] = my[d];
+            __syncwarp();
+        }
+    }
+}
+
+int launch_tile_histograms(const uint32_t* keys, uint64_t n, int r, int bit_group, int block, uint32_t* hist,
+                           cudaStream_t s)
+{
+    if (n == 0) return LSD_OK;
+    const uint64_t tiles = (n + (uint64_t)block - 1) / (uint64_t)block;
+    const int shift = bit_group * r;
+    const uint64_t want = (tiles + (kTileHistThreads / 32) - 1) / (kTileHistThreads / 32);
+    const uint64_t cap = (uint64_t)sm_count() * 8 * 4;  // enough resident warps; the rest by grid stride
+    const int grid = (int)(want < cap ? want : cap);
+    switch (r) {
+        case 1: tile_hist_kernel<1><<<grid, kTileHistThreads, 0, s>>>(keys, n, shift, (uint32_t)block, tiles, hist); break;
+        case 2: tile_hist_kernel<2><<<grid, kTileHistThreads, 0, s>>>(keys, n, shift, (uint32_t)block, tiles, hist); break;
+        case 4: tile_hist_kernel<4><<<grid, kTileHistThreads, 0, s>>>(keys, n, shift, (uint32_t)block, tiles, hist); break;
+        case 8: tile_hist_kernel<8><<<grid, kTileHistThreads, 0, s>>>(keys, n, shift, (uint32_t)block, tiles, hist); break;
+        default: return LSD_ERR_INVALID_VALUE;
+    }
+    LSD_LAUNCH_CHECK();
+    return LSD_OK;
+}
+
+}  // namespace lsd

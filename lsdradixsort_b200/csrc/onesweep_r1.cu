@@ -1,0 +1,19 @@
+// onesweep_r1.cu -- kernel shapes for 1-bit digits (32 passes).  Entry 0 is the default.
+#include "onesweep.cuh"
+
+namespace lsd {
+
+static const OnesweepLauncher kTable[] = {
+    make_launcher<1, 256, 16, kMatchBallot>(),
+    make_launcher<1, 128, 16, kMatchBallot>(),
+    make_launcher<1, 512, 16, kMatchBallot>(),
+    make_launcher<1, 1024, 8, kMatchBallot>(),
+};
+
+const OnesweepLauncher* onesweep_table_r1(int* count)
+{
+    *count = (int)(sizeof(kTable) / sizeof(kTable[0]));
+    return kTable;
+}
+
+}  // namespace lsd

@@ -1,0 +1,19 @@
+// onesweep_r2.cu -- kernel shapes for 2-bit digits (16 passes).  Entry 0 is the default.
+#include "onesweep.cuh"
+
+namespace lsd {
+
+static const OnesweepLauncher kTable[] = {
+    make_launcher<2, 256, 16, kMatchBallot>(),
+    make_launcher<2, 128, 16, kMatchBallot>(),
+    make_launcher<2, 512, 16, kMatchBallot>(),
+    make_launcher<2, 1024, 8, kMatchBallot>(),
+};
+
+const OnesweepLauncher* onesweep_table_r2(int* count)
+{
+    *count = (int)(sizeof(kTable) / sizeof(kTable[0]));
+    return kTable;
+}
+
+}  // namespace lsd

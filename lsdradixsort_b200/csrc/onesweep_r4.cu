@@ -1,0 +1,19 @@
+// onesweep_r4.cu -- kernel shapes for 4-bit digits (8 passes).  Entry 0 is the default.
+#include "onesweep.cuh"
+
+namespace lsd {
+
+static const OnesweepLauncher kTable[] = {
+    make_launcher<4, 256, 16, kMatchBallot>(),
+    make_launcher<4, 128, 16, kMatchBallot>(),
+    make_launcher<4, 512, 16, kMatchBallot>(),
+    make_launcher<4, 1024, 8, kMatchBallot>(),
+};
+
+const OnesweepLauncher* onesweep_table_r4(int* count)
+{
+    *count = (int)(sizeof(kTable) / sizeof(kTable[0]));
+    return kTable;
+}
+
+}  // namespace lsd

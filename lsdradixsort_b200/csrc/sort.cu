@@ -1,0 +1,212 @@
+// sort.cu -- host orchestration of the LSD sort: workspace layout, device-side plan, pass loop.
+//
+// Replaces GPULSDRadixSort (LSDRadixSort.cu:839-910).  Where the reference launches ~16 kernels
+// plus a D2D copy per pass and creates/destroys two streams per call, this enqueues, on the
+// caller's stream and without any host synchronisation:
+//     memset(workspace) -> digit_hist_kernel -> plan_kernel -> onesweep_kernel x passes -> copy_back_kernel
+// Pass skipping and ping-pong parity are decided ON THE DEVICE by plan_kernel (every pass kernel
+// reads the plan and exits at once if its digit is constant), so the sequence is fixed, fully
+// asynchronous and CUDA-graph capturable.
+#include <algorithm>
+
+#include "onesweep.cuh"
+#include "sort.h"
+
+namespace lsd {
+
+// -------------------------------------------------------------------------------------
+// plan_kernel: one CTA.  For every pass: skip flag (some bucket holds all n keys), exclusive
+// scan of the digit histogram -> absolute bucket bases (uint64), ping-pong parity.
+// -------------------------------------------------------------------------------------
+constexpr int kPlanThreads = 256;
+
+__global__ void __launch_bounds__(kPlanThreads)
+plan_kernel(const uint64_t* __restrict__ hist, uint64_t* __restrict__ bases, SortPlan* __restrict__ plan, uint64_t n,
+            int passes, int H, int disable_skip)
+{
+    __shared__ uint64_t s_warp[kPlanThreads / 32];
+    __shared__ uint32_t s_parity;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    if (tid == 0) s_parity = 0;
+    __syncthreads();
+    uint32_t executed = 0;
+    for (int p = 0; p < passes; ++p) {
+        const uint64_t v = (int)tid < H ? hist[p * H + tid] : 0ull;
+        const int full = __syncthreads_or(v == n);
+        uint64_t incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint64_t t = __shfl_up_sync(kFullMask, incl, o);
+            if (lane >= (uint32_t)o) incl += t;
+        }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        uint64_t prefix = 0;
+        for (uint32_t w = 0; w < warp; ++w) prefix += s_warp[w];
+        if ((int)tid < H) bases[(size_t)(2 * p) * H + tid] = prefix + incl - v;
+        if (tid == 0) {
+            const uint32_t skip = (full && !disable_skip) ? 1u : 0u;
+            plan->skip[p] = skip;
+            plan->src_is_scratch[p] = s_parity;
+            if (!skip) { s_parity ^= 1u; ++executed; }
+        }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        plan->result_in_scratch = s_parity;
+        plan->executed_passes = executed;
+    }
+}
+
+// copy_back_kernel: only does work when an odd number of passes ran (result sits in scratch).
+__global__ void __launch_bounds__(256)
+copy_back_kernel(uint32_t* __restrict__ keys, const uint32_t* __restrict__ scratch, uint64_t n,
+                 const SortPlan* __restrict__ plan)
+{
+    if (!plan->result_in_scratch) return;
+    const uint64_t nvec = n >> 2;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride)
+        reinterpret_cast<uint4*>(keys)[i] = reinterpret_cast<const uint4*>(scratch)[i];
+    if (blockIdx.x == 0) {
+        const uint64_t t = (nvec << 2) + threadIdx.x;
+        if (t < n) keys[t] = scratch[t];
+    }
+}
+
+// -------------------------------------------------------------------------------------
+// shape selection and workspace layout
+// -------------------------------------------------------------------------------------
+static const OnesweepLauncher* table_for(int r, int* count)
+{
+    switch (r) {
+        case 1: return onesweep_table_r1(count);
+        case 2: return onesweep_table_r2(count);
+        case 4: return onesweep_table_r4(count);
+        case 8: return onesweep_table_r8(count);
+    }
+    *count = 0;
+    return nullptr;
+}
+
+const OnesweepLauncher* select_launcher(int r, int block, uint32_t variant)
+{
+    int count = 0;
+    const OnesweepLauncher* t = table_for(r, &count);
+    if (!t) return nullptr;
+    if (variant != 0) return variant < (uint32_t)count ? &t[variant] : nullptr;
+    if (block <= 0) return &t[0];
+    const OnesweepLauncher* best = nullptr;
+    for (int i = 0; i < count; ++i) {
+        if (t[i].mode != t[0].mode) continue;
+        if (t[i].threads == block) return &t[i];
+        if (!best || std::abs(t[i].threads - block) < std::abs(best->threads - block)) best = &t[i];
+    }
+    return best;
+}
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+int make_layout(uint64_t n, int r, int block, const lsd_sort_options* opt, SortLayout* L)
+{
+    if (!valid_radix(r)) return LSD_ERR_INVALID_VALUE;
+    if (block < 0 || block > 1024) return LSD_ERR_INVALID_VALUE;
+    if (n >= (1ull << 32)) return LSD_ERR_UNSUPPORTED;  // 32-bit scatter indices in this build
+    const uint32_t variant = opt ? opt->variant : 0u;
+    const OnesweepLauncher* k = select_launcher(r, block, variant);
+    if (!k) return LSD_ERR_INVALID_VALUE;
+    L->k = k;
+    L->passes = 32 / r;
+    L->H = 1 << r;
+    uint32_t portion = k->portion_max;
+    if (opt && opt->portion_keys) {
+        // round the requested portion down to whole tiles (at least one tile)
+        uint64_t want = std::max<uint64_t>(k->tile, (uint64_t)opt->portion_keys / k->tile * k->tile);
+        portion = (uint32_t)std::min<uint64_t>(want, k->portion_max);
+    }
+    L->portion_keys = portion;
+    L->portions = n ? (n + portion - 1) / portion : 0;
+    L->total_tiles = 0;
+    for (uint64_t q = 0; q < L->portions; ++q) {
+        const uint64_t keys = std::min<uint64_t>(portion, n - q * portion);
+        L->total_tiles += (keys + k->tile - 1) / k->tile;
+    }
+    size_t off = 0;
+    L->off_plan = off;     off = align_up(off + sizeof(SortPlan), 256);
+    L->off_hist = off;     off = align_up(off + sizeof(uint64_t) * L->passes * L->H, 256);
+    L->off_bases = off;    off = align_up(off + sizeof(uint64_t) * 2 * L->passes * L->H, 256);
+    L->off_tickets = off;  off = align_up(off + sizeof(uint32_t) * L->passes * std::max<uint64_t>(1, L->portions), 256);
+    L->off_lookback = off; off = align_up(off + sizeof(uint32_t) * L->passes * L->total_tiles * L->H, 256);
+    L->total_bytes = off;
+    return LSD_OK;
+}
+
+// -------------------------------------------------------------------------------------
+// the sort
+// -------------------------------------------------------------------------------------
+int sort_enqueue(uint32_t* keys, uint32_t* scratch, uint64_t n, int r, int block, void* ws, size_t ws_bytes,
+                 const lsd_sort_options* opt, cudaStream_t s, cudaEvent_t* events, int* launches)
+{
+    SortLayout L;
+    const int st = make_layout(n, r, block, opt, &L);
+    if (st != LSD_OK) return st;
+    if (launches) *launches = 0;
+    if (n == 0) return LSD_OK;
+    if (!keys || !scratch || !ws) return LSD_ERR_INVALID_VALUE;
+    if (ws_bytes < L.total_bytes) return LSD_ERR_WORKSPACE_TOO_SMALL;
+    if (!aligned_to(keys, 16) || !aligned_to(scratch, 16) || !aligned_to(ws, 256)) return LSD_ERR_ALIGNMENT;
+
+    char* w = static_cast<char*>(ws);
+    SortPlan* plan = reinterpret_cast<SortPlan*>(w + L.off_plan);
+    uint64_t* hist = reinterpret_cast<uint64_t*>(w + L.off_hist);
+    uint64_t* bases = reinterpret_cast<uint64_t*>(w + L.off_bases);
+    uint32_t* tickets = reinterpret_cast<uint32_t*>(w + L.off_tickets);
+    uint32_t* lookback = reinterpret_cast<uint32_t*>(w + L.off_lookback);
+
+    int ev = 0, nl = 0;
+    if (events) LSD_CUDA_TRY(cudaEventRecord(events[ev++], s));
+    LSD_CUDA_TRY(cudaMemsetAsync(ws, 0, L.total_bytes, s));
+    int rc = launch_digit_histograms(keys, n, r, hist, s);
+    if (rc != LSD_OK) return rc;
+    ++nl;
+    plan_kernel<<<1, kPlanThreads, 0, s>>>(hist, bases, plan, n, L.passes, L.H, opt ? (int)opt->disable_skip : 0);
+    LSD_LAUNCH_CHECK();
+    ++nl;
+    if (events) LSD_CUDA_TRY(cudaEventRecord(events[ev++], s));
+
+    for (int p = 0; p < L.passes; ++p) {
+        uint32_t* lb = lookback + (size_t)p * L.total_tiles * L.H;
+        for (uint64_t q = 0; q < L.portions; ++q) {
+            const uint64_t pbase = q * (uint64_t)L.portion_keys;
+            const uint32_t pkeys = (uint32_t)std::min<uint64_t>(L.portion_keys, n - pbase);
+            PassArgs a;
+            a.keys = keys;
+            a.scratch = scratch;
+            a.plan = plan;
+            a.bases_in = bases + (size_t)(2 * p + (q & 1)) * L.H;
+            a.bases_out = (q + 1 < L.portions) ? bases + (size_t)(2 * p + ((q + 1) & 1)) * L.H : nullptr;
+            a.lookback = lb;
+            a.ticket = tickets + (size_t)p * L.portions + q;
+            a.portion_base = pbase;
+            a.portion_keys = pkeys;
+            a.tiles = (pkeys + L.k->tile - 1) / L.k->tile;
+            a.pass = p;
+            a.shift = p * r;
+            rc = L.k->launch(a, s);
+            if (rc != LSD_OK) return rc;
+            ++nl;
+            lb += (size_t)a.tiles * L.H;
+        }
+        if (events) LSD_CUDA_TRY(cudaEventRecord(events[ev++], s));
+    }
+
+    const int copy_grid = (int)std::min<uint64_t>((uint64_t)sm_count() * 8, ((n >> 2) + 255) / 256 + 1);
+    copy_back_kernel<<<copy_grid, 256, 0, s>>>(keys, scratch, n, plan);
+    LSD_LAUNCH_CHECK();
+    ++nl;
+    if (events) LSD_CUDA_TRY(cudaEventRecord(events[ev++], s));
+    if (launches) *launches = nl;
+    return LSD_OK;
+}
+
+}  // namespace lsd
