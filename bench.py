@@ -1,0 +1,408 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the LSD radix sort hot path (BASELINE.json metric).
+
+    python bench.py --gpus 1 --steps K --warmup W                  # our arm, one B200
+    torchrun --nproc-per-node N ... bench.py --gpus N ...          # our arm, N ranks (NCCL)
+    python bench.py --impl reference --gpus N --steps K --warmup W # the reference's CPU path
+
+One "step" = one full sort of the workload's keys (synthetic uniform uint32):
+  N = 1 : 2^28 keys on one GPU, 8-bit digits, 4 passes        (BASELINE configs[1])
+  N > 1 : 2^32 keys in total, 2^32/N per rank before the exchange (BASELINE configs[4])
+`value`   = keys sorted per second over all ranks, keys resident in HBM when the clock starts.
+`e2e`     = same metric through the host-buffer C-ABI call (lsd_sort_host: H2D + sort + D2H inside).
+`roofline`= the dominant kernel (one onesweep digit pass): 8 B/key algorithmic bytes per launch over
+            its CUDA-event duration, against the measured HBM copy bandwidth.
+`cpu_baseline` = the reference's own CPU LSDRadixSort (compiled from /root/reference into oracle/_ref),
+            timed on this box's host cores (it is single-threaded).
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+
+METRIC = "uint32_lsd_sort_throughput"
+UNIT = "Gkeys/s"
+R_BITS = 8
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--log2n", type=int, default=0, help="override keys per step (total over ranks), log2")
+    ap.add_argument("--block", type=int, default=0)
+    ap.add_argument("--variant", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-baseline-log2n", type=int, default=28)
+    return ap.parse_args()
+
+
+def workload(args):
+    n_gpus = max(1, args.gpus)
+    if args.log2n:
+        total = 1 << args.log2n
+    else:
+        total = (1 << 28) if n_gpus == 1 else (1 << 32)
+    name = (f"LSD radix sort of 2^{total.bit_length() - 1} uniform uint32 keys, r=8 (4 passes), "
+            + ("1xB200" if n_gpus == 1 else f"{n_gpus}xB200: MSD-histogram all-reduce + all-to-all bucket exchange + local LSD"))
+    return total, name
+
+
+# ----------------------------------------------------------------------------------------------
+# helpers
+# ----------------------------------------------------------------------------------------------
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:  # noqa: BLE001
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic(kernel_key: str):
+    p = ROOT / "profiles" / "ncu_traffic.json"
+    if p.exists():
+        try:
+            return json.loads(p.read_text()).get(kernel_key, {}).get("dram_bytes_per_launch")
+        except Exception:  # noqa: BLE001
+            return None
+    return None
+
+
+def cpu_reference_sort_gkeys(log2n: int, reps: int = 1):
+    """Time the reference's CPU LSDRadixSort (r=8) on 2^log2n uniform keys.  Returns (Gkeys/s, kind)."""
+    import numpy as np
+
+    import _oracle
+    from lsdradixsort_b200 import keygen
+
+    n = 1 << log2n
+    keys = keygen.uniform_u32(n, seed=0)
+    ref = _oracle.ref()
+    best = None
+    for _ in range(reps):
+        a, b, h = keys.copy(), np.empty_like(keys), np.zeros(1 << R_BITS, dtype=np.uint32)
+        t0 = time.perf_counter()
+        if ref is not None:
+            ref.ref_cpu_sort(a, b, n, h, R_BITS)
+        else:
+            _oracle.oracle().lsd_oracle_sort(a, b, n, h, R_BITS)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    assert bool(np.all(b[:-1] <= b[1:])), "CPU reference produced an unsorted array"
+    return n / best / 1e9, ("reference" if ref is not None else "port")
+
+
+# ----------------------------------------------------------------------------------------------
+# reference arm: the reference's own CPU implementation of the path, on the host cores
+# ----------------------------------------------------------------------------------------------
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    total, name = workload(args)
+    sample_log2 = 26  # bounded sample of the workload: ~2.5 s of CPU per step
+    vals = []
+    kind = "port"
+    for i in range(args.warmup + args.steps):
+        g, kind = cpu_reference_sort_gkeys(sample_log2)
+        if i >= args.warmup:
+            vals.append(g)
+    value = sum(vals) / len(vals)
+    ms = (1 << sample_log2) / value / 1e6
+    sample = (f"2^{sample_log2} uniform uint32 keys per step (bounded sample of the 2^{total.bit_length() - 1}-key workload), "
+              "LSDRadixSort r=8 from LSDRadixSort.cu:62-69, single-threaded as written")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": round(value, 5), "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 3), "higher_is_better": True,
+        "scaling": "weak" if args.gpus == 1 else "strong", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+        "config": {"workload": name, "reference_path": "CPU (the reference's GPU path needs its unchecked preconditions; "
+                   "its CPU LSDRadixSort is the implementation of record)"},
+        "cpu_baseline": {"value": round(value, 5), "unit": UNIT, "cores": 1, "kind": kind, "sample": sample,
+                         "host_cores_available": os.cpu_count()},
+        "e2e": {"value": round(value, 5), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+# ----------------------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import lsdradixsort_b200 as L
+    from lsdradixsort_b200 import multi
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (impl=ours) needs a GPU: the product has no CPU path")
+    L.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    distributed = world > 1
+    if distributed:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    total, name = workload(args)
+    n_local = total // world
+    opts = {"variant": args.variant} if args.variant else {}
+
+    def barrier():
+        if distributed:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    src = torch.empty(n_local, dtype=torch.int32, device=dev)
+    chunk = 1 << 26
+    for lo in range(0, n_local, chunk):  # bounded temporaries: randint works in int64
+        hi = min(n_local, lo + chunk)
+        src[lo:hi] = torch.randint(-(2**31), 2**31, (hi - lo,), dtype=torch.int64, device=dev, generator=g).to(torch.int32)
+    work = torch.empty_like(src)
+
+    if distributed:
+        capacity = int(n_local * 1.25) + (1 << 16)
+        ops = multi.CudaOps(capacity, r=R_BITS, block=args.block)
+        recv = torch.empty(capacity, dtype=torch.int32, device=dev)
+        staging = torch.empty(n_local, dtype=torch.int32, device=dev)
+        sorter = ops.sorter
+
+        def step():
+            return multi.distributed_sort(work, ops, recv, staging)
+    else:
+        sorter = L.Sorter(n_local, r=R_BITS, block=args.block, **opts)
+
+        def step():
+            sorter.sort_(work)
+            return work, None
+
+    ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    for _ in range(args.warmup):
+        work.copy_(src)
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    stats = None
+    out = work
+    for i in range(args.steps):
+        work.copy_(src)  # restore the unsorted input (not timed; 2 x n x 4 B also flushes nothing we rely on:
+        if distributed:  # the key buffers are far larger than the 126 MB L2)
+            dist.barrier()
+        ev0[i].record()
+        out, stats = step()
+        ev1[i].record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    step_ms = [a.elapsed_time(b) for a, b in zip(ev0, ev1)]
+    mean_ms = sum(step_ms) / len(step_ms)
+    t = torch.tensor([mean_ms], dtype=torch.float64, device=dev)
+    if distributed:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_per_step = float(t.item())
+    value = total / (ms_per_step * 1e-3) / 1e9
+
+    # ---- correctness of what was just timed: sortedness per rank, boundaries across ranks, key count ----
+    def is_sorted_u32(t):
+        step_keys = 1 << 27
+        for lo in range(0, t.numel(), step_keys):
+            hi = min(t.numel(), lo + step_keys + 1)
+            u = t[lo:hi].to(torch.int64) & 0xFFFFFFFF
+            if u.numel() > 1 and not bool((u[1:] >= u[:-1]).all()):
+                return False
+        return True
+
+    ok = is_sorted_u32(out)
+    if distributed:
+        lo = int(out[0].item()) & 0xFFFFFFFF if out.numel() else 0
+        hi = int(out[-1].item()) & 0xFFFFFFFF if out.numel() else 0
+        edge = torch.tensor([lo, hi, out.numel()], dtype=torch.int64, device=dev)
+        edges = [torch.empty_like(edge) for _ in range(world)]
+        dist.all_gather(edges, edge)
+        e = torch.stack(edges).cpu().tolist()
+        ok = ok and all(e[i][1] <= e[i + 1][0] for i in range(world - 1) if e[i][2] and e[i + 1][2])
+        ok = ok and sum(x[2] for x in e) == total
+        flag = torch.tensor([1 if ok else 0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        ok = bool(flag.item())
+    if not ok:
+        raise SystemExit("bench.py: output is NOT sorted -- refusing to report a number")
+
+    # ---- roofline leg: per-kernel CUDA-event times of the local sort (same keys, same shapes) ----
+    peak, peak_src = measured_peak()
+    n_roof = n_local
+    pass_ms, hist_ms = [], []
+    for i in range(max(3, min(args.steps, 10))):
+        work.copy_(src)
+        st = sorter.sort_timed_(work)
+        if i >= 1:
+            hist_ms.append(st[0])
+            pass_ms += [x for x in st[1:-1] if x > 0]
+    avg_pass = sum(pass_ms) / max(1, len(pass_ms))
+    avg_hist = sum(hist_ms) / max(1, len(hist_ms))
+    achieved = 8.0 * n_roof / (avg_pass * 1e6) if avg_pass > 0 else 0.0
+    sort_ms = 4 * avg_pass + avg_hist
+    traffic = ncu_traffic("onesweep_pass_r8")
+    roofline = {
+        "bound": "hbm", "kernel": "onesweep digit pass (r=8), the dominant kernel: 4 launches per sort",
+        "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
+        "peak_source": peak_src, "algorithmic_bytes_per_launch": 8 * n_roof, "avg_launch_ms": round(avg_pass, 4),
+        "traffic": traffic, "hist_plus_plan_ms": round(avg_hist, 4),
+        "whole_sort": {"algorithmic_bytes": 32 * n_roof, "ms": round(sort_ms, 4),
+                       "frac_of_peak": round(32.0 * n_roof / (sort_ms * 1e6) / peak, 4) if sort_ms > 0 else None},
+    }
+    launches_per_sort = sorter.info(n_roof).launches
+    per_step = launches_per_sort
+    if distributed:  # + top-digit histogram + partition pass (histogram, plan, one launch per portion)
+        per_step += 1 + 2 + max(1, (launches_per_sort - 3) // 4)
+    gpu_launches = args.steps * per_step
+
+    # ---- e2e: host buffers through the C ABI, copies inside the timed region ----
+    e2e = None
+    if not distributed:
+        hs = L.HostSorter(n_local, r=R_BITS, block=args.block)
+        pinned_src = src.cpu().pin_memory()
+        pinned = torch.empty_like(pinned_src).pin_memory()
+        e2e_steps = max(1, min(args.steps, 10))
+        ts = []
+        for i in range(2 + e2e_steps):
+            pinned.copy_(pinned_src)
+            t0 = time.perf_counter()
+            hs.sort_(pinned)  # blocking: H2D + sort + D2H
+            dt = time.perf_counter() - t0
+            if i >= 2:
+                ts.append(dt)
+        hs.close()
+        e2e_ms = 1e3 * sum(ts) / len(ts)
+        e2e = {"value": round(n_local / (e2e_ms * 1e-3) / 1e9, 3), "unit": UNIT, "h2d_bytes_per_step": 4 * n_local,
+               "d2h_bytes_per_step": 4 * n_local, "ms_per_step": round(e2e_ms, 3), "steps": e2e_steps,
+               "api": "lsd_sort_host (C ABI, pinned host buffer)", "timer": "host wall clock around the blocking call"}
+    else:
+        pinned_src = src.cpu().pin_memory()
+        pinned_out = torch.empty(recv.numel(), dtype=torch.int32).pin_memory()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ts = []
+        for i in range(1 + min(args.steps, 3)):
+            barrier()
+            a.record()
+            work.copy_(pinned_src, non_blocking=True)
+            o, _ = multi.distributed_sort(work, ops, recv, staging)
+            pinned_out[: o.numel()].copy_(o, non_blocking=True)
+            b.record()
+            torch.cuda.synchronize()
+            if i >= 1:
+                ts.append(a.elapsed_time(b))
+        tt = torch.tensor([sum(ts) / len(ts)], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_ms = float(tt.item())
+        e2e = {"value": round(total / (e2e_ms * 1e-3) / 1e9, 3), "unit": UNIT, "h2d_bytes_per_step": 4 * n_local,
+               "d2h_bytes_per_step": 4 * int(out.numel()), "ms_per_step": round(e2e_ms, 3),
+               "api": "multi.distributed_sort with pinned host buffers per rank", "timer": "CUDA events, max over ranks"}
+
+    cpu_baseline = None
+    if rank == 0 and not distributed and not args.no_cpu_baseline:
+        gk, kind = cpu_reference_sort_gkeys(args.cpu_baseline_log2n)
+        cpu_baseline = {"value": round(gk, 5), "unit": UNIT, "cores": 1, "kind": kind,
+                        "sample": f"2^{args.cpu_baseline_log2n} uniform uint32 keys, 1 run of the reference's CPU LSDRadixSort "
+                                  "(r=8, LSDRadixSort.cu:62-69; single-threaded as written)",
+                        "host_cores_available": os.cpu_count()}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": round(ms_per_step, 4), "higher_is_better": True,
+            "scaling": "strong" if distributed else "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+            "config": {"workload": name, "keys_total": total, "keys_per_rank": n_local, "radix_bits": R_BITS,
+                       "block": args.block, "variant": args.variant,
+                       "l2": "inputs larger than L2 (>= 1 GiB of keys per rank vs 126 MB); input restored before every step",
+                       "timing": "CUDA events around each step on the launching stream, mean over steps, max over ranks",
+                       "published_reference": "0.400 Gkeys/s (RTX 3060 Ti, 2^30 keys, R=4/B=512; BenchmarkLSDRadixSort.md:153-161)"},
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": gpu_launches,
+            "clocks": clocks, "verified_sorted": True,
+        }
+        if stats is not None:
+            line["exchange"] = {"sent_bytes_rank0": stats.sent_bytes, "recv_bytes_rank0": stats.recv_bytes,
+                                "keys_owned_rank0": stats.n_out}
+        print(json.dumps(line))
+    if distributed:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

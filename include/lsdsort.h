@@ -116,6 +116,15 @@ LSD_API int lsd_sort(uint32_t *keys, uint32_t *scratch, uint64_t n, int r, int b
 LSD_API int lsd_sort_ex(uint32_t *keys, uint32_t *scratch, uint64_t n, int r, int block, void *ws, size_t ws_bytes,
                         const lsd_sort_options *opt, lsd_stream_t stream);
 
+/* One stable counting-sort pass on digit `bit_group`: out <- in reordered by that digit, keys with
+ * equal digits keeping their input order.  Replaces one iteration of the reference's pass loop
+ * (LSDRadixSort.cu:845-906; CPU twin LSDRadixSortPass, :25-54, without its copy-back at :53).
+ * in and out must not overlap.  If hist_out is non-NULL it receives the 2^r bucket START offsets
+ * (uint64, what the CPU twin leaves in `histogram`).  Workspace: lsd_sort_workspace_bytes(n, r, block).
+ * Also the MSD partition step of the multi-GPU sort (bit_group = 32/r - 1). */
+LSD_API int lsd_sort_pass(const uint32_t *in, uint32_t *out, uint64_t n, int r, int bit_group, int block, void *ws,
+                          size_t ws_bytes, uint64_t *hist_out, lsd_stream_t stream);
+
 /* Same as lsd_sort_ex, but brackets every kernel with CUDA events on `stream`, synchronises,
  * and reports per-stage device times.  stage_ms[0] = digit histogram + plan, stage_ms[1+p] =
  * pass p (0 if skipped), stage_ms[1+passes] = copy-back (0 if none).  Measurement aid for

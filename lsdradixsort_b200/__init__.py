@@ -18,6 +18,7 @@ from .api import (  # noqa: F401
     prefix_sum_,
     set_device,
     sort_,
+    sort_pass,
     sort_workspace_bytes,
 )
 

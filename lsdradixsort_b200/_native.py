@@ -79,6 +79,7 @@ def lib() -> C.CDLL:
         "lsd_sort_workspace_bytes_ex": (C.c_size_t, [C.c_uint64, C.c_int, C.c_int, C.POINTER(SortOptions)]),
         "lsd_sort": (C.c_int, [vp, vp, C.c_uint64, C.c_int, C.c_int, vp, C.c_size_t, vp]),
         "lsd_sort_ex": (C.c_int, [vp, vp, C.c_uint64, C.c_int, C.c_int, vp, C.c_size_t, C.POINTER(SortOptions), vp]),
+        "lsd_sort_pass": (C.c_int, [vp, vp, C.c_uint64, C.c_int, C.c_int, C.c_int, vp, C.c_size_t, vp, vp]),
         "lsd_sort_timed": (
             C.c_int,
             [vp, vp, C.c_uint64, C.c_int, C.c_int, vp, C.c_size_t, C.POINTER(SortOptions), vp,

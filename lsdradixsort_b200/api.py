@@ -139,6 +139,27 @@ def GPULSDRadixSort(a: torch.Tensor, b: torch.Tensor, h: torch.Tensor, count: in
     )
 
 
+def sort_pass(src: torch.Tensor, dst: torch.Tensor, r: int, bit_group: int, block: int = 0,
+              workspace: Optional[torch.Tensor] = None, want_offsets: bool = False):
+    """One stable counting-sort pass on digit ``bit_group``: ``dst <- src`` reordered (reference
+    LSDRadixSortPass, .cu:25-54, without the copy-back).  Returns the bucket start offsets if asked."""
+    _check_keys(src, "src")
+    _check_keys(dst, "dst")
+    n = src.numel()
+    if dst.numel() < n:
+        raise ValueError("dst too small")
+    if workspace is None:
+        workspace = torch.empty(max(sort_workspace_bytes(n, r, block), 256), dtype=torch.uint8, device=src.device)
+    offs = torch.empty(1 << r, dtype=torch.int64, device=src.device) if want_offsets else None
+    N.check(
+        N.lib().lsd_sort_pass(src.data_ptr(), dst.data_ptr(), n, r, bit_group, block, workspace.data_ptr(),
+                              workspace.numel(), offs.data_ptr() if offs is not None else None,
+                              _stream_ptr(src.device)),
+        "lsd_sort_pass",
+    )
+    return offs
+
+
 @dataclass
 class SortInfo:
     skipped_mask: int

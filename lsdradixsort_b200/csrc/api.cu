@@ -139,6 +139,13 @@ LSD_API int lsd_sort(uint32_t* keys, uint32_t* scratch, uint64_t n, int r, int b
     return lsd_sort_ex(keys, scratch, n, r, block, ws, ws_bytes, nullptr, stream);
 }
 
+LSD_API int lsd_sort_pass(const uint32_t* in, uint32_t* out, uint64_t n, int r, int bit_group, int block, void* ws,
+                          size_t ws_bytes, uint64_t* hist_out, lsd_stream_t stream)
+{
+    if (!valid_radix(r)) return LSD_ERR_INVALID_VALUE;
+    return pass_enqueue(in, out, n, r, bit_group, block, ws, ws_bytes, hist_out, (cudaStream_t)stream);
+}
+
 LSD_API int lsd_sort_timed(uint32_t* keys, uint32_t* scratch, uint64_t n, int r, int block, void* ws, size_t ws_bytes,
                            const lsd_sort_options* opt, lsd_stream_t stream, float* stage_ms, int stage_cap,
                            int* stages_written)

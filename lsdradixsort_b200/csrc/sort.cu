@@ -209,4 +209,88 @@ int sort_enqueue(uint32_t* keys, uint32_t* scratch, uint64_t n, int r, int block
     return LSD_OK;
 }
 
+
+// -------------------------------------------------------------------------------------
+// single pass (lsd_sort_pass): digit histogram of the whole input -> plan with skipping disabled
+// (pass `bit_group` reads `in`, writes `out`) -> one onesweep launch per portion.
+// -------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kPlanThreads)
+single_pass_plan_kernel(const uint64_t* __restrict__ hist, uint64_t* __restrict__ bases, SortPlan* __restrict__ plan,
+                        uint64_t* __restrict__ hist_out, int pass, int H)
+{
+    __shared__ uint64_t s_warp[kPlanThreads / 32];
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const uint64_t v = (int)tid < H ? hist[pass * H + tid] : 0ull;
+    uint64_t incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint64_t t = __shfl_up_sync(kFullMask, incl, o);
+        if (lane >= (uint32_t)o) incl += t;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    uint64_t prefix = 0;
+    for (uint32_t w = 0; w < warp; ++w) prefix += s_warp[w];
+    if ((int)tid < H) {
+        bases[(size_t)(2 * pass) * H + tid] = prefix + incl - v;
+        if (hist_out) hist_out[tid] = prefix + incl - v;
+    }
+    if (tid == 0) {
+        plan->skip[pass] = 0;
+        plan->src_is_scratch[pass] = 0;  // PassArgs.keys = in, PassArgs.scratch = out
+    }
+}
+
+int pass_enqueue(const uint32_t* in, uint32_t* out, uint64_t n, int r, int bit_group, int block, void* ws,
+                 size_t ws_bytes, uint64_t* hist_out, cudaStream_t s)
+{
+    SortLayout L;
+    const int st = make_layout(n, r, block, nullptr, &L);
+    if (st != LSD_OK) return st;
+    if (bit_group < 0 || bit_group >= L.passes) return LSD_ERR_INVALID_VALUE;
+    if (n == 0) {
+        if (hist_out) LSD_CUDA_TRY(cudaMemsetAsync(hist_out, 0, sizeof(uint64_t) * L.H, s));
+        return LSD_OK;
+    }
+    if (!in || !out || !ws) return LSD_ERR_INVALID_VALUE;
+    if (ws_bytes < L.total_bytes) return LSD_ERR_WORKSPACE_TOO_SMALL;
+    if (!aligned_to(in, 16) || !aligned_to(out, 16) || !aligned_to(ws, 256)) return LSD_ERR_ALIGNMENT;
+
+    char* w = static_cast<char*>(ws);
+    SortPlan* plan = reinterpret_cast<SortPlan*>(w + L.off_plan);
+    uint64_t* hist = reinterpret_cast<uint64_t*>(w + L.off_hist);
+    uint64_t* bases = reinterpret_cast<uint64_t*>(w + L.off_bases);
+    uint32_t* tickets = reinterpret_cast<uint32_t*>(w + L.off_tickets);
+    uint32_t* lookback = reinterpret_cast<uint32_t*>(w + L.off_lookback);
+    // only this pass's slice of tickets / look-back words is used, but zeroing up to its end is simplest
+    const size_t lb_words_per_pass = (size_t)L.total_tiles * L.H;
+    LSD_CUDA_TRY(cudaMemsetAsync(ws, 0, L.off_lookback + sizeof(uint32_t) * lb_words_per_pass, s));
+    int rc = launch_digit_histograms(in, n, r, hist, s);
+    if (rc != LSD_OK) return rc;
+    single_pass_plan_kernel<<<1, kPlanThreads, 0, s>>>(hist, bases, plan, hist_out, bit_group, L.H);
+    LSD_LAUNCH_CHECK();
+    uint32_t* lb = lookback;
+    for (uint64_t q = 0; q < L.portions; ++q) {
+        const uint64_t pbase = q * (uint64_t)L.portion_keys;
+        const uint32_t pkeys = (uint32_t)std::min<uint64_t>(L.portion_keys, n - pbase);
+        PassArgs a;
+        a.keys = const_cast<uint32_t*>(in);
+        a.scratch = out;
+        a.plan = plan;
+        a.bases_in = bases + (size_t)(2 * bit_group + (q & 1)) * L.H;
+        a.bases_out = (q + 1 < L.portions) ? bases + (size_t)(2 * bit_group + ((q + 1) & 1)) * L.H : nullptr;
+        a.lookback = lb;
+        a.ticket = tickets + q;
+        a.portion_base = pbase;
+        a.portion_keys = pkeys;
+        a.tiles = (pkeys + L.k->tile - 1) / L.k->tile;
+        a.pass = bit_group;
+        a.shift = bit_group * r;
+        rc = L.k->launch(a, s);
+        if (rc != LSD_OK) return rc;
+        lb += (size_t)a.tiles * L.H;
+    }
+    return LSD_OK;
+}
+
 }  // namespace lsd

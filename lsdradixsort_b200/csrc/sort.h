@@ -23,4 +23,8 @@ int make_layout(uint64_t n, int r, int block, const lsd_sort_options* opt, SortL
 int sort_enqueue(uint32_t* keys, uint32_t* scratch, uint64_t n, int r, int block, void* ws, size_t ws_bytes,
                  const lsd_sort_options* opt, cudaStream_t s, cudaEvent_t* events, int* launches);
 
+// One stable pass on `bit_group` from `in` to `out` (no plan, never skipped).
+int pass_enqueue(const uint32_t* in, uint32_t* out, uint64_t n, int r, int bit_group, int block, void* ws,
+                 size_t ws_bytes, uint64_t* hist_out, cudaStream_t s);
+
 }  // namespace lsd

@@ -251,3 +251,57 @@ def test_digit_histograms_tiny():
         d = dev(keys) if n else torch.empty(0, dtype=torch.int32, device="cuda")
         got = L.digit_histograms(d, 8).cpu().numpy().astype(np.uint64)
         assert np.array_equal(got, _oracle.digit_histograms(keys, 8))
+
+
+# ------------------------------------------------------------------------------------------
+# single pass (lsd_sort_pass): stability is observable here, unlike in the full keys-only sort
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("r,bit_group", [(8, 0), (8, 3), (4, 5), (2, 9), (1, 17), (1, 31)])
+@pytest.mark.parametrize("n", [1, 1000, 123_457])
+def test_sort_pass_matches_reference_pass(r, bit_group, n):
+    """One pass == the reference's LSDRadixSortPass (.cu:25-54): keys with equal digits keep input order."""
+    keys = keygen.make_keys("uniform", n, seed=r * 100 + bit_group)
+    src, dst = dev(keys), torch.zeros(n, dtype=torch.int32, device="cuda")
+    offs = L.sort_pass(src, dst, r, bit_group, want_offsets=True)
+    a, want, hist = keys.copy(), np.zeros_like(keys), np.zeros(1 << r, dtype=np.uint32)
+    _oracle.oracle().lsd_oracle_sort_pass(a, want, n, hist, r, bit_group)
+    assert np.array_equal(host(dst), want)
+    assert np.array_equal(host(src), keys)  # input untouched
+    assert np.array_equal(offs.cpu().numpy().astype(np.uint32), hist)  # bucket starts, as the CPU twin leaves them
+
+
+def test_sort_pass_chain_equals_full_sort():
+    n = 50_000
+    keys = keygen.make_keys("entropy4_table", n, 8)
+    a, b = dev(keys), torch.empty(n, dtype=torch.int32, device="cuda")
+    for g in range(4):
+        L.sort_pass(a, b, 8, g)
+        a, b = b, a
+    assert np.array_equal(host(a), np.sort(keys))
+
+
+def test_multi_gpu_ops_single_rank_roundtrip():
+    """CudaOps (the device half of multi.distributed_sort) on one GPU with a 1-rank gloo group."""
+    import torch.distributed as dist
+
+    from lsdradixsort_b200 import multi
+
+    n = 200_000
+    keys = keygen.make_keys("uniform", n, 77)
+    if not dist.is_initialized():
+        dist.init_process_group("gloo", init_method="tcp://127.0.0.1:29571", rank=0, world_size=1)
+    try:
+        ops = multi.CudaOps(n + 1024, r=8)
+        d = dev(keys)
+        recv, staging = ops.empty(n + 1024), ops.empty(n)
+        # gloo moves CPU tensors only; with one rank the exchange is the identity, so emulate it on device
+        hist = ops.top_digit_histogram(d).cpu().numpy()
+        assert np.array_equal(hist.astype(np.uint64), _oracle.digit_histograms(keys, 8)[-1])
+        ops.partition_by_top_digit(d, staging)
+        part = host(staging)
+        assert np.array_equal(part >> 24, np.sort(keys >> 24))  # grouped by destination bucket
+        recv[:n].copy_(staging)
+        ops.sort_(recv[:n])
+        assert np.array_equal(host(recv[:n]), np.sort(keys))
+    finally:
+        dist.destroy_process_group()
