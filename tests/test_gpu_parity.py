@@ -85,10 +85,11 @@ def test_sort_skip_disabled_gives_same_result():
     assert np.array_equal(host(d), _oracle.sort(keys, 8))
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5, 6, 7])
-def test_sort_kernel_variants_r8(variant):
+@pytest.mark.parametrize("kind", ["uniform", "entropy4_table", "all_equal"])
+@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13])
+def test_sort_kernel_variants_r8(variant, kind):
     n = 300_000 + 11
-    keys = keygen.make_keys("uniform", n, seed=variant)
+    keys = keygen.make_keys(kind, n, seed=variant)
     d = dev(keys)
     L.sort_(d, r=8, variant=variant)
     assert np.array_equal(host(d), _oracle.sort(keys, 8))
