@@ -107,6 +107,8 @@ typedef struct lsd_sort_options {
     uint32_t portion_keys;  /* 0 = default; max keys per look-back portion (tests use small values) */
     uint32_t disable_skip;  /* 1 = run every pass even if its digit is constant */
     uint32_t variant;       /* 0 = default kernel shape; other values select tuning variants */
+    uint64_t debug_trace;   /* 0, or a device pointer to 16 uint64 per tile of the LAST pass: per-phase SM clocks
+                               (tuning aid, only honoured by kernels that support it) */
 } lsd_sort_options;
 
 LSD_API size_t lsd_sort_workspace_bytes(uint64_t n, int r, int block);

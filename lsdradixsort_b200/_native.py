@@ -35,6 +35,7 @@ class SortOptions(C.Structure):
         ("portion_keys", C.c_uint32),
         ("disable_skip", C.c_uint32),
         ("variant", C.c_uint32),
+        ("debug_trace", C.c_uint64),
     ]
 
 

@@ -35,10 +35,12 @@ def _check_keys(t: torch.Tensor, what: str) -> None:
         raise ValueError(f"{what} must be a contiguous 1-D tensor")
 
 
-def _options(portion_keys: int = 0, disable_skip: bool = False, variant: int = 0) -> Optional[N.SortOptions]:
-    if not (portion_keys or disable_skip or variant):
+def _options(portion_keys: int = 0, disable_skip: bool = False, variant: int = 0,
+             debug_trace: int = 0) -> Optional[N.SortOptions]:
+    if not (portion_keys or disable_skip or variant or debug_trace):
         return None
-    return N.SortOptions(C.sizeof(N.SortOptions), int(portion_keys), int(bool(disable_skip)), int(variant))
+    return N.SortOptions(C.sizeof(N.SortOptions), int(portion_keys), int(bool(disable_skip)), int(variant),
+                         int(debug_trace))
 
 
 def set_device(index: int) -> None:

@@ -58,6 +58,7 @@ struct PassArgs {
     uint32_t tiles;            // tiles in this portion
     int pass;
     int shift;
+    unsigned long long* trace;  // optional per-tile phase clocks (tuning aid), else nullptr
 };
 
 enum MatchMode { kMatchBallot = 0, kMatchHw = 1 };

@@ -115,6 +115,7 @@ onesweep_lpc_kernel(const PassArgs a)
     constexpr int SCAN_WARPS = S_::ROW_GROUPS < WARPS ? S_::ROW_GROUPS : WARPS;  // warps 0.. own the matrix rows
     constexpr int DT0 = THREADS - ROWS;  // digit-pair threads are the LAST `ROWS` threads of the CTA: they enter the
                                          // rank chain last, so their look-back overlaps the chain of the first warps
+    constexpr int LB = 8;                  // look-back window (predecessor rows fetched per round trip)
     constexpr uint32_t kScanBarrier = 15;  // named barrier: "scan pass 2 done" among the scan warps
 
     if (a.plan->skip[a.pass]) return;
@@ -246,14 +247,28 @@ onesweep_lpc_kernel(const PassArgs a)
     if (digit_thread) {
         uint32_t ex_lo = 0, ex_hi = 0;
         if (tile > 0) {
+            // Windowed walk: LB predecessors are fetched at once (independent loads), then consumed in order
+            // until an INCLUSIVE word is met; a not-yet-published predecessor restarts the window there.
             const uint32_t* p = a.lookback + (size_t)(tile - 1) * H + 2 * dt;
-            while (true) {
-                const uint2 w = ld_relaxed_gpu_v2(p);
-                if (w.x == 0) continue;  // predecessor not published yet
-                ex_lo += w.x & kLbValueMask;
-                ex_hi += w.y & kLbValueMask;
-                if (w.x & kLbGlobal) break;
-                p -= H;
+            uint32_t remaining = tile;  // predecessors that exist: tile-1 .. 0 (tile 0 is always INCLUSIVE)
+            bool done = false;
+            while (!done) {
+                uint2 w[LB];
+#pragma unroll
+                for (int b = 0; b < LB; ++b)
+                    w[b] = (uint32_t)b < remaining ? ld_relaxed_gpu_v2(p - (size_t)b * H) : make_uint2(0u, 0u);
+                uint32_t consumed = 0;
+#pragma unroll
+                for (int b = 0; b < LB; ++b) {
+                    if (!done && consumed == (uint32_t)b && w[b].x != 0) {
+                        ex_lo += w[b].x & kLbValueMask;
+                        ex_hi += w[b].y & kLbValueMask;
+                        ++consumed;
+                        if (w[b].x & kLbGlobal) done = true;
+                    }
+                }
+                p -= (size_t)consumed * H;
+                remaining -= consumed;
             }
             st_relaxed_gpu_v2(lb_row + 2 * dt, kLbGlobal | (ex_lo + cnt_lo), kLbGlobal | (ex_hi + cnt_hi));
         }

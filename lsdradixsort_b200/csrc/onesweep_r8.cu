@@ -1,12 +1,13 @@
 // onesweep_r8.cu -- kernel shapes for 8-bit digits (4 passes): the headline configuration.
 // Entry 0 is the default; the others are reachable through `block` (threads per CTA, the
 // reference's B) and lsd_sort_options.variant (tuning sweeps from bench_tools/).
-#include "onesweep_lpc.cuh"
+#include "onesweep_lpc32.cuh"
+#include "onesweep_lpcp.cuh"
 
 namespace lsd {
 
 static const OnesweepLauncher kTable[] = {
-    make_launcher<8, 512, 16, kMatchBallot>(),   // 0: default
+    make_lpc32_launcher<8, 9, 29, 3>(),          // 0: default -- LPC ranking, 32-bit byte-offset counters (= variant 19)
     make_launcher<8, 128, 24, kMatchBallot>(),   // 1
     make_launcher<8, 256, 24, kMatchBallot>(),   // 2
     make_launcher<8, 1024, 8, kMatchBallot>(),   // 3
@@ -20,6 +21,21 @@ static const OnesweepLauncher kTable[] = {
     make_lpc_launcher<8, 9, 29, 2>(),            // 11: as 8 with 2 CTAs/SM register budget
     make_lpc_launcher<8, 13, 19, 2>(),           // 12: 416 threads, tile 7904
     make_lpc_launcher<8, 9, 15, 4>(),            // 13: 288 threads, tile 4320
+    make_lpcp_launcher<8, 9, 29, 2>(),           // 14: persistent pipelined, 9 worker + 4 look-back warps, tile 8352
+    make_lpcp_launcher<8, 7, 37, 2>(),           // 15: 7 worker warps, tile 8288
+    make_lpcp_launcher<8, 11, 23, 2>(),          // 16: 11 worker warps, tile 8096
+    make_lpcp_launcher<8, 5, 51, 2>(),           // 17: 5 worker warps, tile 8160
+    make_lpcp_launcher<8, 9, 15, 3>(),           // 18: tile 4320, 3 CTAs/SM
+    make_lpc32_launcher<8, 9, 29, 3>(),          // 19: 32-bit byte-offset counters, compile-time shift, tile 8352
+    make_lpc32_launcher<8, 11, 23, 3>(),         // 20: 352 threads, tile 8096
+    make_lpc32_launcher<8, 13, 19, 3>(),         // 21: 416 threads, tile 7904
+    make_lpc32_launcher<8, 9, 29, 2>(),          // 22: as 19 with the 2-CTA register budget
+    make_lpc32_launcher<8, 9, 17, 4>(),          // 23: tile 4896, 4 CTAs/SM
+    make_lpc_launcher<8, 9, 29, 4>(),            // 24: packed counters, 56-register budget, 4 CTAs/SM
+    make_lpc32_launcher<8, 9, 21, 3>(),          // 25: tile 6048
+    make_lpc_launcher<8, 9, 21, 4>(),            // 26: packed, tile 6048, 4 CTAs/SM
+    make_lpc_launcher<8, 9, 23, 4>(),            // 27: packed, tile 6624, 4 CTAs/SM
+    make_launcher<8, 512, 16, kMatchBallot>(),   // 28: warp-multisplit (ballot) kernel, the round-1 v1 default
 };
 
 const OnesweepLauncher* onesweep_table_r8(int* count)

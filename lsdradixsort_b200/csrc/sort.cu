@@ -96,10 +96,11 @@ const OnesweepLauncher* select_launcher(int r, int block, uint32_t variant)
     if (!t) return nullptr;
     if (variant != 0) return variant < (uint32_t)count ? &t[variant] : nullptr;
     if (block <= 0) return &t[0];
+    // `block` is the reference's threads-per-block knob: pick the warp-multisplit shape with exactly that many
+    // threads if there is one, else the shape (of any family) whose CTA size is closest.
     const OnesweepLauncher* best = nullptr;
     for (int i = 0; i < count; ++i) {
-        if (t[i].mode != t[0].mode) continue;
-        if (t[i].threads == block) return &t[i];
+        if (t[i].mode == kMatchBallot && t[i].threads == block) return &t[i];
         if (!best || std::abs(t[i].threads - block) < std::abs(best->threads - block)) best = &t[i];
     }
     return best;
@@ -192,6 +193,8 @@ int sort_enqueue(uint32_t* keys, uint32_t* scratch, uint64_t n, int r, int block
             a.tiles = (pkeys + L.k->tile - 1) / L.k->tile;
             a.pass = p;
             a.shift = p * r;
+            a.trace = (opt && opt->debug_trace && p == L.passes - 1 && q == 0)
+                          ? reinterpret_cast<unsigned long long*>(opt->debug_trace) : nullptr;
             rc = L.k->launch(a, s);
             if (rc != LSD_OK) return rc;
             ++nl;
@@ -286,6 +289,7 @@ int pass_enqueue(const uint32_t* in, uint32_t* out, uint64_t n, int r, int bit_g
         a.tiles = (pkeys + L.k->tile - 1) / L.k->tile;
         a.pass = bit_group;
         a.shift = bit_group * r;
+        a.trace = nullptr;
         rc = L.k->launch(a, s);
         if (rc != LSD_OK) return rc;
         lb += (size_t)a.tiles * L.H;
