@@ -57,15 +57,14 @@ __device__ __forceinline__ uint32_t cell_offset(uint32_t key, uint32_t lane4)
     return (x & mask) | lane4;
 }
 
-template <int RB, int WARPS, int ITEMS, int MINB, int SHIFT>
+template <int RB, int WARPS, int ITEMS, int MINB, int SHIFT, int LB>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
 onesweep_lpc32_kernel(const PassArgs a)
 {
     using S_ = Lpc32Shape<RB, WARPS, ITEMS>;
     constexpr int H = S_::H, THREADS = S_::THREADS, S = S_::S, TILE = S_::TILE;
     constexpr int SW = S_::SW, GPW = S_::GPW, LBT = S_::LBT, LBW = S_::LBW;
-    constexpr int LB = 8;
-    constexpr uint32_t kBarTot = 14, kBarScan = 15;
+    constexpr uint32_t kBarTot = 14, kBarScan = 15;  // LB = look-back window (rows fetched per round trip)
 
     if (a.plan->skip[a.pass]) return;
 
@@ -240,7 +239,9 @@ onesweep_lpc32_kernel(const PassArgs a)
                 const uint32_t* p = lb_row - H + 2 * dt;
                 uint32_t remaining = tile;
                 bool done = false;
+                uint32_t dbg_rounds = 0, dbg_hops = 0;
                 while (!done) {
+                    ++dbg_rounds;
                     uint2 w[LB];
 #pragma unroll
                     for (int k = 0; k < LB; ++k)
@@ -257,6 +258,11 @@ onesweep_lpc32_kernel(const PassArgs a)
                     }
                     p -= (size_t)consumed * H;
                     remaining -= consumed;
+                    dbg_hops += consumed;
+                }
+                if (a.trace && warp == (uint32_t)WARPS - 1 && lane == 0) {
+                    a.trace[(size_t)tile * 16 + 13] = dbg_rounds;
+                    a.trace[(size_t)tile * 16 + 14] = dbg_hops;
                 }
                 st_relaxed_gpu_v2(lb_row + 2 * dt, kLbGlobal | (ex_lo + cnt_lo), kLbGlobal | (ex_hi + cnt_hi));
             }
@@ -317,11 +323,11 @@ onesweep_lpc32_kernel(const PassArgs a)
 #undef LSD_TRACE
 }
 
-template <int RB, int WARPS, int ITEMS, int MINB, int SHIFT>
+template <int RB, int WARPS, int ITEMS, int MINB, int SHIFT, int LB>
 int onesweep_lpc32_launch_shift(const PassArgs& a, cudaStream_t s)
 {
     using S_ = Lpc32Shape<RB, WARPS, ITEMS>;
-    auto kern = onesweep_lpc32_kernel<RB, WARPS, ITEMS, MINB, SHIFT>;
+    auto kern = onesweep_lpc32_kernel<RB, WARPS, ITEMS, MINB, SHIFT, LB>;
     LSD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S_::SMEM_BYTES));
     LSD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     kern<<<a.tiles, S_::THREADS, S_::SMEM_BYTES, s>>>(a);
@@ -329,27 +335,27 @@ int onesweep_lpc32_launch_shift(const PassArgs& a, cudaStream_t s)
     return LSD_OK;
 }
 
-template <int RB, int WARPS, int ITEMS, int MINB>
+template <int RB, int WARPS, int ITEMS, int MINB, int LB>
 int onesweep_lpc32_launch(const PassArgs& a, cudaStream_t s)
 {
     static_assert(RB == 8, "shift dispatch below is written for 8-bit digits");
     switch (a.shift) {
-        case 0: return onesweep_lpc32_launch_shift<RB, WARPS, ITEMS, MINB, 0>(a, s);
-        case 8: return onesweep_lpc32_launch_shift<RB, WARPS, ITEMS, MINB, 8>(a, s);
-        case 16: return onesweep_lpc32_launch_shift<RB, WARPS, ITEMS, MINB, 16>(a, s);
-        case 24: return onesweep_lpc32_launch_shift<RB, WARPS, ITEMS, MINB, 24>(a, s);
+        case 0: return onesweep_lpc32_launch_shift<RB, WARPS, ITEMS, MINB, 0, LB>(a, s);
+        case 8: return onesweep_lpc32_launch_shift<RB, WARPS, ITEMS, MINB, 8, LB>(a, s);
+        case 16: return onesweep_lpc32_launch_shift<RB, WARPS, ITEMS, MINB, 16, LB>(a, s);
+        case 24: return onesweep_lpc32_launch_shift<RB, WARPS, ITEMS, MINB, 24, LB>(a, s);
     }
     return LSD_ERR_INVALID_VALUE;
 }
 
 constexpr int kModeLpc32 = 4;
 
-template <int RB, int WARPS, int ITEMS, int MINB>
+template <int RB, int WARPS, int ITEMS, int MINB, int LB = 8>
 constexpr OnesweepLauncher make_lpc32_launcher()
 {
     using S_ = Lpc32Shape<RB, WARPS, ITEMS>;
     return OnesweepLauncher{RB, S_::THREADS, ITEMS, kModeLpc32, (uint32_t)S_::TILE, S_::PORTION_MAX, S_::SMEM_BYTES,
-                            &onesweep_lpc32_launch<RB, WARPS, ITEMS, MINB>};
+                            &onesweep_lpc32_launch<RB, WARPS, ITEMS, MINB, LB>};
 }
 
 }  // namespace lsd

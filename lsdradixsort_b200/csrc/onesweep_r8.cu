@@ -3,11 +3,13 @@
 // reference's B) and lsd_sort_options.variant (tuning sweeps from bench_tools/).
 #include "onesweep_lpc32.cuh"
 #include "onesweep_lpcp.cuh"
+#include "onesweep_cpc.cuh"
+#include "onesweep_cpcp.cuh"
 
 namespace lsd {
 
 static const OnesweepLauncher kTable[] = {
-    make_lpc32_launcher<8, 9, 29, 3>(),          // 0: default -- LPC ranking, 32-bit byte-offset counters (= variant 19)
+    make_lpc32_launcher<8, 9, 29, 3, 4>(),       // 0: default -- LPC ranking, 32-bit byte-offset counters, look-back window 4 (= variant 30)
     make_launcher<8, 128, 24, kMatchBallot>(),   // 1
     make_launcher<8, 256, 24, kMatchBallot>(),   // 2
     make_launcher<8, 1024, 8, kMatchBallot>(),   // 3
@@ -36,6 +38,25 @@ static const OnesweepLauncher kTable[] = {
     make_lpc_launcher<8, 9, 21, 4>(),            // 26: packed, tile 6048, 4 CTAs/SM
     make_lpc_launcher<8, 9, 23, 4>(),            // 27: packed, tile 6624, 4 CTAs/SM
     make_launcher<8, 512, 16, kMatchBallot>(),   // 28: warp-multisplit (ballot) kernel, the round-1 v1 default
+    make_lpc32_launcher<8, 9, 29, 3, 16>(),      // 29: look-back window 16
+    make_lpc32_launcher<8, 9, 29, 3, 4>(),       // 30: look-back window 4
+    make_lpc32_launcher<8, 9, 29, 3, 2>(),       // 31: look-back window 2
+    make_cpc_launcher<8, 64, 3, 8>(),            // 32: column-private counters, 128 threads, tile 8192, 3 CTAs/SM
+    make_cpc_launcher<8, 64, 3, 16>(),           // 33: look-back window 16
+    make_cpc_launcher<8, 64, 3, 4>(),            // 34: look-back window 4
+    make_cpc_launcher<8, 48, 3, 8>(),            // 35: tile 6144
+    make_cpc_launcher<8, 32, 4, 8>(),            // 36: tile 4096, 4 CTAs/SM
+    make_cpc_launcher<8, 64, 3, 0>(),            // 37: TIMING EXPERIMENT, no look-back (output wrong)
+    make_cpc_launcher<8, 64, 3, 32>(),           // 38: look-back window 32
+    make_cpc_launcher<8, 64, 3, 0, 2>(),         // 39: TIMING: no look-back, full-line stores
+    make_cpc_launcher<8, 64, 3, 0, 4>(),         // 40: TIMING: no look-back, no global stores
+    make_cpc_launcher<8, 64, 3, 0, 8>(),         // 41: TIMING: no look-back, conflict-free smem scatter
+    make_cpc_launcher<8, 64, 3, 0, 10>(),        // 42: TIMING: no look-back, conflict-free scatter, full-line stores
+    make_cpc_launcher<8, 64, 3, 0, 12>(),        // 43: TIMING: no look-back, conflict-free scatter, no stores
+    make_cpcp_launcher<8, 64, 4, 8, 152>(),      // 44: persistent pipeline, 4 buffers, front groups at 152 registers
+    make_cpcp_launcher<8, 64, 4, 8, 0>(),        // 45: same without register reallocation
+    make_cpcp_launcher<8, 64, 4, 4, 152>(),      // 46: look-back window 4
+    make_cpcp_launcher<8, 48, 5, 8, 0>(),        // 47: tile 6144, 5 buffers, no register reallocation
 };
 
 const OnesweepLauncher* onesweep_table_r8(int* count)

@@ -5,7 +5,9 @@
 // is read once and written once (8 B per element), in place, uint32 wrap-around like the
 // reference.
 //
-// Tile = THREADS x 16 elements.  Each thread loads four 128-bit vectors in a vector-striped
+// Tile = THREADS x 32 elements (round 1 started with 16: ncu showed the kernel latency-bound on the
+// look-back, 65 K tiles starting every ~22 cycles; larger tiles space the tile starts out so that one
+// 32-wide window covers the tiles in flight).  Each thread loads eight 128-bit vectors in a vector-striped
 // arrangement (vector j of thread t sits at vector index j*THREADS + t of the tile), so every
 // warp load is one contiguous 512-byte run.  Tile order is handed out by an atomic ticket, so a
 // tile only ever waits on tiles that are already running (forward progress without relying on
@@ -16,7 +18,7 @@
 
 namespace lsd {
 
-constexpr int kScanItems = 16;  // elements per thread (4 x uint4)
+constexpr int kScanItems = 32;  // elements per thread (8 x uint4)
 constexpr int kScanVecs = kScanItems / 4;
 
 constexpr uint64_t kFlagAggregate = 1ull << 32;
@@ -44,7 +46,9 @@ scan_kernel(uint32_t* __restrict__ a, uint64_t n, ScanWorkspace* __restrict__ ws
 {
     constexpr int WARPS = THREADS / 32;
     constexpr int TILE = THREADS * kScanItems;
-    static_assert(kScanVecs * WARPS <= 64, "cross-warp scan assumes at most 64 partials");
+    constexpr int P = kScanVecs * WARPS;   // per-(vector, warp) partial sums, scanned by warp 0
+    constexpr int PPL = P / 32;            // partials per lane of warp 0
+    static_assert(P % 32 == 0 && PPL >= 1, "partials must fill warp 0 evenly");
 
     __shared__ uint32_t s_tile;
     __shared__ uint32_t s_partial[kScanVecs * WARPS];  // [vec j][warp] inclusive sums
@@ -66,7 +70,7 @@ scan_kernel(uint32_t* __restrict__ a, uint64_t n, ScanWorkspace* __restrict__ ws
     if (full) {
 #pragma unroll
         for (int j = 0; j < kScanVecs; ++j)
-            v[j] = *reinterpret_cast<const uint4*>(a + base + 4ull * (j * THREADS + tid));
+            v[j] = __ldcs(reinterpret_cast<const uint4*>(a + base + 4ull * (j * THREADS + tid)));
     } else {
 #pragma unroll
         for (int j = 0; j < kScanVecs; ++j) {
@@ -88,16 +92,22 @@ scan_kernel(uint32_t* __restrict__ a, uint64_t n, ScanWorkspace* __restrict__ ws
     __syncthreads();
 
     if (warp == 0) {
-        // scan the kScanVecs*WARPS partials (<= 64) with one warp, two per lane
-        constexpr int P = kScanVecs * WARPS;
-        const uint32_t i0 = 2 * lane, i1 = 2 * lane + 1;
-        const uint32_t p0 = i0 < P ? s_partial[i0] : 0u;
-        const uint32_t p1 = i1 < P ? s_partial[i1] : 0u;
-        const uint32_t pair_incl = warp_inclusive_scan(p0 + p1, lane);
-        const uint32_t pair_excl = pair_incl - (p0 + p1);
-        const uint32_t tile_total = __shfl_sync(kFullMask, pair_incl, 31);
-        if (i0 < P) s_partial[i0] = pair_excl;       // exclusive prefix of partial i0
-        if (i1 < P) s_partial[i1] = pair_excl + p0;  // exclusive prefix of partial i1
+        // scan the P partials with one warp, PPL consecutive partials per lane
+        uint32_t part[PPL];
+        uint32_t lane_sum = 0;
+#pragma unroll
+        for (int k = 0; k < PPL; ++k) {
+            part[k] = s_partial[lane * PPL + k];
+            lane_sum += part[k];
+        }
+        const uint32_t lane_incl = warp_inclusive_scan(lane_sum, lane);
+        const uint32_t tile_total = __shfl_sync(kFullMask, lane_incl, 31);
+        uint32_t run = lane_incl - lane_sum;
+#pragma unroll
+        for (int k = 0; k < PPL; ++k) {
+            s_partial[lane * PPL + k] = run;  // exclusive prefix of this partial
+            run += part[k];
+        }
 
         // ---- decoupled look-back ----
         uint32_t exclusive = 0;
@@ -108,21 +118,26 @@ scan_kernel(uint32_t* __restrict__ a, uint64_t n, ScanWorkspace* __restrict__ ws
             int64_t look = (int64_t)tile - 1;
             while (true) {
                 const int64_t idx = look - (int64_t)lane;
-                uint64_t w;
-                do {  // virtual tiles before tile 0 read as "inclusive prefix 0"
-                    w = idx >= 0 ? ld_relaxed_gpu(&ws->state[idx]) : kFlagInclusive;
-                } while (__any_sync(kFullMask, (w >> 32) == 0));
+                // virtual tiles before tile 0 read as "inclusive prefix 0"
+                const uint64_t w = idx >= 0 ? ld_relaxed_gpu(&ws->state[idx]) : kFlagInclusive;
+                const uint32_t ready = __ballot_sync(kFullMask, (w >> 32) != 0);
                 const uint32_t incl_mask = __ballot_sync(kFullMask, (w >> 32) == 2);
-                const uint32_t val = (uint32_t)w;
-                uint32_t take = val;
+                uint32_t take = (uint32_t)w;
+                bool finished = false;
                 if (incl_mask) {
-                    const uint32_t first = __ffs(incl_mask) - 1;  // nearest tile holding an inclusive prefix
+                    // only the predecessors up to the nearest INCLUSIVE one have to be ready
+                    const uint32_t first = __ffs(incl_mask) - 1;
+                    const uint32_t need = (2u << first) - 1u;
+                    if ((ready & need) != need) continue;  // poll again
                     if (lane > first) take = 0;
+                    finished = true;
+                } else if (ready != kFullMask) {
+                    continue;  // window not complete yet and no inclusive word in sight: poll again
                 }
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) take += __shfl_xor_sync(kFullMask, take, o);
                 exclusive += take;
-                if (incl_mask) break;
+                if (finished) break;
                 look -= 32;
             }
             if (lane == 0) st_relaxed_gpu(&ws->state[tile], kFlagInclusive | (uint32_t)(exclusive + tile_total));
@@ -144,7 +159,7 @@ scan_kernel(uint32_t* __restrict__ a, uint64_t n, ScanWorkspace* __restrict__ ws
         o.w = run;
         const uint64_t e = 4ull * (j * THREADS + tid);
         if (full) {
-            *reinterpret_cast<uint4*>(a + base + e) = o;
+            __stcs(reinterpret_cast<uint4*>(a + base + e), o);
         } else {
             if (e + 0 < left) a[base + e + 0] = o.x;
             if (e + 1 < left) a[base + e + 1] = o.y;
