@@ -306,3 +306,62 @@ def test_multi_gpu_ops_single_rank_roundtrip():
         assert np.array_equal(host(recv[:n]), np.sort(keys))
     finally:
         dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------
+# third parity leg: the reference's OWN CUDA kernels (oracle/_ref, rebuilt for sm_100a, unmodified)
+# ------------------------------------------------------------------------------------------
+def _ref_or_skip():
+    ref = _oracle.ref()
+    if ref is None:
+        pytest.skip("oracle/_ref/libref_lsd.so not present (built in the container from /root/reference)")
+    return ref
+
+
+@pytest.mark.parametrize("r,block", [(8, 1024), (8, 256), (4, 512), (1, 128)])
+def test_sort_matches_reference_gpu(r, block):
+    """Bit-exact against GPULSDRadixSort (.cu:839) called directly (its TestGPU... wrapper would SKIP r=8, .cu:940),
+    under its preconditions: count % block == 0, powers of two."""
+    ref = _ref_or_skip()
+    n = 1 << 20
+    keys = keygen.make_keys("uniform", n, seed=77 + r)
+    grid = n // block
+    a, b = dev(keys), torch.empty(n, dtype=torch.int32, device="cuda")
+    h = torch.empty(3 * grid * (1 << r), dtype=torch.int32, device="cuda")
+    bs = torch.empty(ref.ref_block_sums_count(grid * (1 << r), block) + 64, dtype=torch.int32, device="cuda")
+    assert ref.ref_gpu_sort(a.data_ptr(), b.data_ptr(), h.data_ptr(), bs.data_ptr(), n, block, r) == 0
+    assert ref.ref_device_synchronize() == 0
+    ours = dev(keys)
+    L.sort_(ours, r=r, block=block)
+    assert np.array_equal(host(ours), host(a))
+    assert np.array_equal(host(ours), np.sort(keys))
+
+
+@pytest.mark.parametrize("block", [128, 256, 512])
+def test_prefix_sum_matches_reference_gpu(block):
+    """GPUPrefixSum (.cu:286) vs lsd_prefix_sum on the same words (the reference's own check is .cu:364)."""
+    ref = _ref_or_skip()
+    n = 1 << 20
+    words = keygen.make_keys("uniform", n, seed=block)
+    a = dev(words)
+    bs = torch.empty(ref.ref_block_sums_count(n, block) + 64, dtype=torch.int32, device="cuda")
+    assert ref.ref_gpu_prefix_sum(a.data_ptr(), n, block, bs.data_ptr()) == 0
+    assert ref.ref_device_synchronize() == 0
+    ours = dev(words)
+    L.prefix_sum_(ours, block)
+    assert np.array_equal(host(ours), host(a))
+
+
+@pytest.mark.parametrize("r,block", [(1, 128), (8, 256), (8, 512)])
+def test_build_histogram_matches_reference_gpu(r, block):
+    """BuildHistogramsKernel (.cu:660) vs lsd_build_histogram, reference layout [G][2^r] (its own check is .cu:785)."""
+    ref = _ref_or_skip()
+    n = 1 << 20
+    keys = keygen.make_keys("uniform", n, seed=r + block)
+    a = dev(keys)
+    grid = n // block
+    h = torch.empty(grid * (1 << r), dtype=torch.int32, device="cuda")
+    assert ref.ref_gpu_build_histograms(a.data_ptr(), h.data_ptr(), n, r, 1 if r == 8 else 3, block) == 0
+    assert ref.ref_device_synchronize() == 0
+    ours = L.build_histogram(a, r, 1 if r == 8 else 3, block)
+    assert torch.equal(ours.view(-1), h)
