@@ -45,6 +45,8 @@ def parse_args():
     ap.add_argument("--log2n", type=int, default=0, help="override keys per step (total over ranks), log2")
     ap.add_argument("--block", type=int, default=0)
     ap.add_argument("--variant", type=int, default=0)
+    ap.add_argument("--exchange", choices=["peer", "nccl"], default="peer",
+                    help="N>1: fused partition+exchange over NVLink peer stores (default) or partition + NCCL all_to_all")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-baseline-log2n", type=int, default=28)
     return ap.parse_args()
@@ -57,7 +59,7 @@ def workload(args):
     else:
         total = (1 << 28) if n_gpus == 1 else (1 << 32)
     name = (f"LSD radix sort of 2^{total.bit_length() - 1} uniform uint32 keys, r=8 (4 passes), "
-            + ("1xB200" if n_gpus == 1 else f"{n_gpus}xB200: MSD-histogram all-reduce + all-to-all bucket exchange + local LSD"))
+            + ("1xB200" if n_gpus == 1 else f"{n_gpus}xB200: MSD-histogram all-reduce + bucket exchange over NVLink + local LSD"))
     return total, name
 
 
@@ -232,9 +234,10 @@ def run_ours(args):
         recv = torch.empty(capacity, dtype=torch.int32, device=dev)
         staging = torch.empty(n_local, dtype=torch.int32, device=dev)
         sorter = ops.sorter
+        peer = multi.PeerExchange(recv) if args.exchange == "peer" else None
 
         def step():
-            return multi.distributed_sort(work, ops, recv, staging)
+            return multi.distributed_sort(work, ops, recv, staging, peer=peer)
     else:
         sorter = L.Sorter(n_local, r=R_BITS, block=args.block, **opts)
 
@@ -321,9 +324,29 @@ def run_ours(args):
     }
     launches_per_sort = sorter.info(n_roof).launches
     per_step = launches_per_sort
-    if distributed:  # + top-digit histogram + partition pass (histogram, plan, one launch per portion)
-        per_step += 1 + 2 + max(1, (launches_per_sort - 3) // 4)
+    if distributed:  # + top-digit histogram + partition pass (histogram unless fused, plan, one launch per portion)
+        per_step += 1 + (1 if peer is not None else 2) + max(1, (launches_per_sort - 3) // 4)
     gpu_launches = args.steps * per_step
+
+    # ---- exchange leg (N > 1): per-stage device times of one more step, NVLink roofline of the exchange ----
+    exchange = None
+    if distributed:
+        work.copy_(src)
+        barrier()
+        _, st_x = multi.distributed_sort(work, ops, recv, staging, timing=True, peer=peer)
+        torch.cuda.synchronize()
+        sm = st_x.stage_ms()
+        xt = torch.tensor([sm["partition"] + sm["all_to_all"], float(st_x.sent_bytes)], dtype=torch.float64, device=dev)
+        dist.all_reduce(xt, op=dist.ReduceOp.MAX)
+        x_ms, x_bytes = float(xt[0].item()), float(xt[1].item())
+        exchange = {"mode": "fused partition+exchange: the top-digit pass kernel stores each rank's keys into the owner's "
+                            "buffer over NVLink peer memory (CUDA IPC), no all-to-all" if peer is not None
+                    else "stable top-digit partition pass + NCCL all_to_all_single",
+                    "stages_ms_rank0": {k: round(v, 3) for k, v in sm.items()},
+                    "partition_plus_exchange_ms_max": round(x_ms, 3), "sent_bytes_per_gpu_max": int(x_bytes),
+                    "nvlink": {"achieved_GBs_per_gpu_out": round(x_bytes / (x_ms * 1e6), 1), "peak_GBs_per_direction": 900.0,
+                               "frac": round(x_bytes / (x_ms * 1e6) / 900.0, 4),
+                               "note": "bytes leaving a GPU / time of the fused pass (which also reads and locally writes the keys)"}}
 
     # ---- e2e: host buffers through the C ABI, copies inside the timed region ----
     e2e = None
@@ -354,7 +377,7 @@ def run_ours(args):
             barrier()
             a.record()
             work.copy_(pinned_src, non_blocking=True)
-            o, _ = multi.distributed_sort(work, ops, recv, staging)
+            o, _ = multi.distributed_sort(work, ops, recv, staging, peer=peer)
             pinned_out[: o.numel()].copy_(o, non_blocking=True)
             b.record()
             torch.cuda.synchronize()
@@ -389,8 +412,8 @@ def run_ours(args):
             "clocks": clocks, "verified_sorted": True,
         }
         if stats is not None:
-            line["exchange"] = {"sent_bytes_rank0": stats.sent_bytes, "recv_bytes_rank0": stats.recv_bytes,
-                                "keys_owned_rank0": stats.n_out}
+            line["exchange"] = dict(exchange or {}, sent_bytes_rank0=stats.sent_bytes, recv_bytes_rank0=stats.recv_bytes,
+                                    keys_owned_rank0=stats.n_out)
         print(json.dumps(line))
     if distributed:
         dist.destroy_process_group()

@@ -127,6 +127,26 @@ LSD_API int lsd_sort_ex(uint32_t *keys, uint32_t *scratch, uint64_t n, int r, in
 LSD_API int lsd_sort_pass(const uint32_t *in, uint32_t *out, uint64_t n, int r, int bit_group, int block, void *ws,
                           size_t ws_bytes, uint64_t *hist_out, lsd_stream_t stream);
 
+/* Peer-scatter form of lsd_sort_pass, the fused partition + exchange step of the multi-GPU sort.  Buckets of digit
+ * `bit_group` are grouped into destination SEGMENTS of consecutive buckets: dst_seg[d] = first | last << 16 names the
+ * segment of bucket d (NULL: every bucket is its own segment) and dst_ptrs[d] its destination (equal for all buckets
+ * of a segment).  The keys of a segment are appended to ((uint32_t*)dst_ptrs[d]) tile after tile, inside a tile in
+ * (bucket, input position) order: deterministic, stable inside a bucket, and with one bucket per segment exactly the
+ * output of lsd_sort_pass.  dst_ptrs / dst_seg are DEVICE arrays of 2^r entries; a pointer may aim into this GPU's
+ * memory or into a peer GPU's buffer opened with lsd_ipc_open, in which case the keys cross NVLink as the pass
+ * kernel's own stores (no separate all-to-all, long contiguous runs per destination).  No reference counterpart (the
+ * reference is single-GPU).  The caller orders the peers (a barrier before the buffers are reused and
+ * after the pass, before they are read).  Workspace: lsd_sort_workspace_bytes(n, r, 0). */
+LSD_API int lsd_sort_pass_scatter(const uint32_t *in, uint64_t n, int r, int bit_group, const uint64_t *dst_ptrs,
+                                  const uint32_t *dst_seg, void *ws, size_t ws_bytes, lsd_stream_t stream);
+
+/* CUDA IPC plumbing for the above (one process per GPU on one node).  lsd_ipc_export: 64 opaque handle bytes for the
+ * allocation that contains dev_ptr plus dev_ptr's offset inside it; send both to the peer process.  lsd_ipc_open:
+ * maps the peer's allocation (peer access enabled lazily) and returns the pointer that corresponds to dev_ptr. */
+LSD_API int lsd_ipc_export(const void *dev_ptr, void *handle64, uint64_t *offset_out);
+LSD_API int lsd_ipc_open(const void *handle64, uint64_t offset, void **peer_ptr_out);
+LSD_API int lsd_ipc_close(void *peer_ptr, uint64_t offset);
+
 /* Same as lsd_sort_ex, but brackets every kernel with CUDA events on `stream`, synchronises,
  * and reports per-stage device times.  stage_ms[0] = digit histogram + plan, stage_ms[1+p] =
  * pass p (0 if skipped), stage_ms[1+passes] = copy-back (0 if none).  Measurement aid for

@@ -18,7 +18,10 @@ from .api import (  # noqa: F401
     prefix_sum_,
     set_device,
     sort_,
+    ipc_export,
+    ipc_open,
     sort_pass,
+    sort_pass_scatter,
     sort_workspace_bytes,
 )
 

@@ -81,6 +81,10 @@ def lib() -> C.CDLL:
         "lsd_sort": (C.c_int, [vp, vp, C.c_uint64, C.c_int, C.c_int, vp, C.c_size_t, vp]),
         "lsd_sort_ex": (C.c_int, [vp, vp, C.c_uint64, C.c_int, C.c_int, vp, C.c_size_t, C.POINTER(SortOptions), vp]),
         "lsd_sort_pass": (C.c_int, [vp, vp, C.c_uint64, C.c_int, C.c_int, C.c_int, vp, C.c_size_t, vp, vp]),
+        "lsd_sort_pass_scatter": (C.c_int, [vp, C.c_uint64, C.c_int, C.c_int, vp, vp, vp, C.c_size_t, vp]),
+        "lsd_ipc_export": (C.c_int, [vp, vp, u64p]),
+        "lsd_ipc_open": (C.c_int, [vp, C.c_uint64, C.POINTER(vp)]),
+        "lsd_ipc_close": (C.c_int, [vp, C.c_uint64]),
         "lsd_sort_timed": (
             C.c_int,
             [vp, vp, C.c_uint64, C.c_int, C.c_int, vp, C.c_size_t, C.POINTER(SortOptions), vp,

@@ -162,6 +162,43 @@ def sort_pass(src: torch.Tensor, dst: torch.Tensor, r: int, bit_group: int, bloc
     return offs
 
 
+def sort_pass_scatter(src: torch.Tensor, dst_ptrs: torch.Tensor, r: int, bit_group: int,
+                      workspace: Optional[torch.Tensor] = None, dst_seg: Optional[torch.Tensor] = None) -> None:
+    """Peer-scatter pass (lsd_sort_pass_scatter): the buckets of digit ``bit_group`` go to the device pointers
+    ``dst_ptrs[d]`` (int64 tensor of 2^r addresses on src's device; local or IPC-opened peer memory), grouped into the
+    segments ``dst_seg[d] = first | last << 16`` (int32 tensor; None = one segment per bucket)."""
+    _check_keys(src, "src")
+    if dst_ptrs.dtype != torch.int64 or not dst_ptrs.is_cuda or dst_ptrs.numel() != (1 << r):
+        raise TypeError("dst_ptrs must be a CUDA int64 tensor with 2^r entries")
+    if dst_seg is not None and (dst_seg.dtype != torch.int32 or not dst_seg.is_cuda or dst_seg.numel() != (1 << r)):
+        raise TypeError("dst_seg must be a CUDA int32 tensor with 2^r entries")
+    n = src.numel()
+    if workspace is None:
+        workspace = torch.empty(max(sort_workspace_bytes(n, r, 0), 256), dtype=torch.uint8, device=src.device)
+    N.check(
+        N.lib().lsd_sort_pass_scatter(src.data_ptr(), n, r, bit_group, dst_ptrs.data_ptr(),
+                                      dst_seg.data_ptr() if dst_seg is not None else None, workspace.data_ptr(),
+                                      workspace.numel(), _stream_ptr(src.device)),
+        "lsd_sort_pass_scatter",
+    )
+
+
+def ipc_export(t: torch.Tensor) -> tuple:
+    """(handle bytes, offset) naming ``t``'s device memory for another process on this node (lsd_ipc_export)."""
+    handle = (C.c_ubyte * 64)()
+    off = C.c_uint64(0)
+    N.check(N.lib().lsd_ipc_export(t.data_ptr(), handle, C.byref(off)), "lsd_ipc_export")
+    return bytes(handle), int(off.value)
+
+
+def ipc_open(handle: bytes, offset: int) -> int:
+    """Device address in THIS process of the peer buffer exported as (handle, offset) (lsd_ipc_open)."""
+    buf = (C.c_ubyte * 64).from_buffer_copy(handle)
+    ptr = C.c_void_p()
+    N.check(N.lib().lsd_ipc_open(buf, offset, C.byref(ptr)), "lsd_ipc_open")
+    return int(ptr.value)
+
+
 @dataclass
 class SortInfo:
     skipped_mask: int

@@ -2,6 +2,9 @@
 #include <new>
 
 #include "onesweep.cuh"
+#include <cuda.h>
+#include <cstring>
+
 #include "sort.h"
 
 namespace lsd {
@@ -144,6 +147,53 @@ LSD_API int lsd_sort_pass(const uint32_t* in, uint32_t* out, uint64_t n, int r, 
 {
     if (!valid_radix(r)) return LSD_ERR_INVALID_VALUE;
     return pass_enqueue(in, out, n, r, bit_group, block, ws, ws_bytes, hist_out, (cudaStream_t)stream);
+}
+
+LSD_API int lsd_sort_pass_scatter(const uint32_t* in, uint64_t n, int r, int bit_group, const uint64_t* dst_ptrs,
+                                  const uint32_t* dst_seg, void* ws, size_t ws_bytes, lsd_stream_t stream)
+{
+    if (!valid_radix(r) || !dst_ptrs) return LSD_ERR_INVALID_VALUE;
+    return pass_enqueue(in, nullptr, n, r, bit_group, 0, ws, ws_bytes, nullptr, (cudaStream_t)stream, dst_ptrs, dst_seg);
+}
+
+// ---- peer memory (one process per GPU, same node): CUDA IPC handles for the exchange buffers --------------
+LSD_API int lsd_ipc_export(const void* dev_ptr, void* handle64, uint64_t* offset_out)
+{
+    if (!dev_ptr || !handle64 || !offset_out) return LSD_ERR_INVALID_VALUE;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle is passed as 64 opaque bytes");
+    cudaIpcMemHandle_t h;
+    LSD_CUDA_TRY(cudaIpcGetMemHandle(&h, const_cast<void*>(dev_ptr)));
+    // the handle names the whole allocation: report where dev_ptr sits inside it
+    // (driver entry point fetched through the runtime: no link-time dependency on libcuda)
+    typedef CUresult (*get_range_fn)(CUdeviceptr*, size_t*, CUdeviceptr);
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    LSD_CUDA_TRY(cudaGetDriverEntryPoint("cuMemGetAddressRange", &fn, cudaEnableDefault, &qres));
+    if (!fn || qres != cudaDriverEntryPointSuccess) return LSD_ERR_CUDA;
+    CUdeviceptr base = 0;
+    size_t size = 0;
+    if (reinterpret_cast<get_range_fn>(fn)(&base, &size, (CUdeviceptr)dev_ptr) != CUDA_SUCCESS) return LSD_ERR_CUDA;
+    *offset_out = (uint64_t)((CUdeviceptr)dev_ptr - base);
+    memcpy(handle64, &h, 64);
+    return LSD_OK;
+}
+
+LSD_API int lsd_ipc_open(const void* handle64, uint64_t offset, void** peer_ptr_out)
+{
+    if (!handle64 || !peer_ptr_out) return LSD_ERR_INVALID_VALUE;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    void* base = nullptr;
+    LSD_CUDA_TRY(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+    *peer_ptr_out = static_cast<char*>(base) + offset;
+    return LSD_OK;
+}
+
+LSD_API int lsd_ipc_close(void* peer_ptr, uint64_t offset)
+{
+    if (!peer_ptr) return LSD_OK;
+    LSD_CUDA_TRY(cudaIpcCloseMemHandle(static_cast<char*>(peer_ptr) - offset));
+    return LSD_OK;
 }
 
 LSD_API int lsd_sort_timed(uint32_t* keys, uint32_t* scratch, uint64_t n, int r, int block, void* ws, size_t ws_bytes,

@@ -59,6 +59,8 @@ struct PassArgs {
     int pass;
     int shift;
     unsigned long long* trace;  // optional per-tile phase clocks (tuning aid), else nullptr
+    const uint64_t* dst_ptrs;   // peer-scatter mode only: [H] device pointers, one per bucket (equal inside a segment)
+    const uint32_t* dst_seg;    // peer-scatter mode only: [H] first | last << 16 bucket of the bucket's segment, or nullptr
 };
 
 enum MatchMode { kMatchBallot = 0, kMatchHw = 1 };
@@ -276,6 +278,7 @@ struct OnesweepLauncher {
     uint32_t portion_max;
     size_t smem_bytes;
     int (*launch)(const PassArgs& a, cudaStream_t s);
+    int (*launch_peer)(const PassArgs& a, cudaStream_t s);  // bucket-pointer scatter (multi-GPU exchange), or nullptr
 };
 
 template <int RB, int THREADS, int ITEMS, int MODE>

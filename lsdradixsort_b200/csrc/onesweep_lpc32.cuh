@@ -40,7 +40,10 @@ struct Lpc32Shape {
     static constexpr int OFF_DP = OFF_TOT + H;           // [H] tile-local bucket starts (keys)
     static constexpr int OFF_GBASE = OFF_DP + H;         // [H]
     static constexpr int OFF_MISC = OFF_GBASE + H;       // [0..15] partials, [32] tile id, [34..35] mbarrier
-    static constexpr int WORDS = OFF_MISC + 64;
+    static constexpr int OFF_DST = OFF_MISC + 64;        // [H] 64-bit bucket destination pointers (peer-scatter mode only)
+    static constexpr int OFF_SEG = OFF_DST + 2 * H;      // [H] first | last << 16 bucket of the bucket's destination segment
+    static constexpr int OFF_HEADS = OFF_SEG + H;        // [H] compact list of segment words, [H] = number of segments
+    static constexpr int WORDS = OFF_HEADS + H + 4;
     static constexpr size_t SMEM_BYTES = sizeof(uint32_t) * WORDS + 16;
     static constexpr uint32_t PORTION_MAX = (uint32_t)((((1u << 30) - 1u) / TILE) * TILE);
 };
@@ -57,7 +60,7 @@ __device__ __forceinline__ uint32_t cell_offset(uint32_t key, uint32_t lane4)
     return (x & mask) | lane4;
 }
 
-template <int RB, int WARPS, int ITEMS, int MINB, int SHIFT, int LB>
+template <int RB, int WARPS, int ITEMS, int MINB, int SHIFT, int LB, int CLR, bool PEER>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
 onesweep_lpc32_kernel(const PassArgs a)
 {
@@ -102,7 +105,37 @@ onesweep_lpc32_kernel(const PassArgs a)
             tma_bulk_g2s(s_keys, in + base, TILE * 4, s_bar);
         }
     }
-    {
+    if constexpr (PEER) {
+        // multi-GPU exchange: bucket d goes to dst_ptrs[d][rank within bucket] -- local or peer (NVLink) memory
+        // Buckets that share a destination SEGMENT (seg[d] = first | last << 16) are written as one contiguous block
+        // per tile -- long runs, whole lines over NVLink -- in (tile, bucket, position) order.
+        uint64_t* s_dst = reinterpret_cast<uint64_t*>(smem + S_::OFF_DST);
+        uint32_t* s_seg = smem + S_::OFF_SEG;
+        for (uint32_t i = tid; i < (uint32_t)H; i += THREADS) {
+            s_dst[i] = a.dst_ptrs[i];
+            s_seg[i] = a.dst_seg ? a.dst_seg[i] : (i | (i << 16));
+        }
+        if (warp == 1) {  // compact list of the segments (their heads), for the line-aligned copy-out
+            uint32_t* s_heads = smem + S_::OFF_HEADS;
+            uint32_t count = 0;
+            for (uint32_t c = 0; c < (uint32_t)H; c += 32) {
+                const uint32_t d = c + lane;
+                const uint32_t g = d < (uint32_t)H ? (a.dst_seg ? a.dst_seg[d] : (d | (d << 16))) : 0xFFFFFFFFu;
+                const bool head = d < (uint32_t)H && (g & 0xFFFFu) == d;
+                const uint32_t m = __ballot_sync(kFullMask, head);
+                if (head) s_heads[count + __popc(m & ((1u << lane) - 1u))] = g;
+                count += __popc(m);
+            }
+            if (lane == 0) s_heads[H] = count;
+        }
+    }
+    if constexpr (CLR == 1) {
+        // zero-fill by the uniform datapath (UMEMSETS): one instruction instead of H*8 128-bit stores through the LSU
+        if (tid == 32) {
+            asm volatile("st.bulk.weak.shared::cta [%0], %1, 0;" ::"r"(smem_u32(s_mat)), "l"((uint64_t)(H * 128)) : "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        }
+    } else {
         uint4* m4 = reinterpret_cast<uint4*>(s_mat);
 #pragma unroll
         for (uint32_t i = tid; i < H * 8; i += THREADS) m4[i] = make_uint4(0, 0, 0, 0);
@@ -228,9 +261,21 @@ onesweep_lpc32_kernel(const PassArgs a)
         if (warp == (uint32_t)WARPS - 1) LSD_TRACE(8);  // look-back starts
         const uint32_t dt = tid - (uint32_t)(THREADS - LBT);
         if (dt < (uint32_t)H / 2) {
-            const uint32_t cnt_lo = s_tot[2 * dt];
+            uint32_t cnt_lo = s_tot[2 * dt];
             uint32_t cnt_hi = s_tot[2 * dt + 1];
             if (dt == (uint32_t)H / 2 - 1) cnt_hi -= pads;  // pads of a ragged last tile are not keys
+            uint32_t dp_lo = s_dp[2 * dt], dp_hi = s_dp[2 * dt + 1];
+            if constexpr (PEER) {
+                // count, look back and place per destination segment: every bucket of a segment carries the segment's
+                // count, so the look-back below yields the segment's exclusive prefix for each of its buckets
+                const uint32_t* s_seg = smem + S_::OFF_SEG;
+                const uint32_t g_lo = s_seg[2 * dt], g_hi = s_seg[2 * dt + 1];
+                const uint32_t e_lo = (g_lo >> 16) + 1u, e_hi = (g_hi >> 16) + 1u;
+                dp_lo = s_dp[g_lo & 0xFFFFu];
+                dp_hi = s_dp[g_hi & 0xFFFFu];
+                cnt_lo = (e_lo < (uint32_t)H ? s_dp[e_lo] : valid) - dp_lo;
+                cnt_hi = (e_hi < (uint32_t)H ? s_dp[e_hi] : valid) - dp_hi;
+            }
             uint32_t ex_lo = 0, ex_hi = 0;
             if (tile == 0) {
                 st_relaxed_gpu_v2(lb_row + 2 * dt, kLbGlobal | cnt_lo, kLbGlobal | cnt_hi);
@@ -267,8 +312,8 @@ onesweep_lpc32_kernel(const PassArgs a)
                 st_relaxed_gpu_v2(lb_row + 2 * dt, kLbGlobal | (ex_lo + cnt_lo), kLbGlobal | (ex_hi + cnt_hi));
             }
             const uint64_t b_lo = a.bases_in[2 * dt], b_hi = a.bases_in[2 * dt + 1];
-            s_gbase[2 * dt] = (uint32_t)b_lo + ex_lo - s_dp[2 * dt];
-            s_gbase[2 * dt + 1] = (uint32_t)b_hi + ex_hi - s_dp[2 * dt + 1];
+            s_gbase[2 * dt] = (uint32_t)b_lo + ex_lo - dp_lo;
+            s_gbase[2 * dt + 1] = (uint32_t)b_hi + ex_hi - dp_hi;
             if (a.bases_out != nullptr && tile == a.tiles - 1) {
                 a.bases_out[2 * dt] = b_lo + ex_lo + cnt_lo;
                 a.bases_out[2 * dt + 1] = b_hi + ex_hi + cnt_hi;
@@ -306,7 +351,25 @@ onesweep_lpc32_kernel(const PassArgs a)
     if (warp == 0) LSD_TRACE(11);  // final barrier passed
 
     // ---- 3. stream the reorder buffer out, coalesced per bucket ----
-    if (valid == (uint32_t)TILE) {
+    if constexpr (PEER) {
+        // one loop per destination segment, warps aligned to the 128-byte lines of the DESTINATION: every store of a
+        // long run is one full line (NVLink packets carry whole lines, no partial sectors)
+        const uint64_t* s_dst = reinterpret_cast<const uint64_t*>(smem + S_::OFF_DST);
+        const uint32_t* s_heads = smem + S_::OFF_HEADS;
+        const uint32_t nseg = s_heads[H];
+        for (uint32_t j = 0; j < nseg; ++j) {
+            const uint32_t g = s_heads[j];
+            const uint32_t d0 = g & 0xFFFFu, e = (g >> 16) + 1u;
+            const uint32_t lo = s_dp[d0];
+            uint32_t hi = e < (uint32_t)H ? s_dp[e] : valid;
+            hi = hi < valid ? hi : valid;
+            uint32_t* dst = reinterpret_cast<uint32_t*>(s_dst[d0]);
+            const uint32_t gb = s_gbase[d0];  // index of tile position p in the destination = gb + p
+            const uint32_t mis = (uint32_t)((reinterpret_cast<uintptr_t>(dst) >> 2) + gb + lo) & 31u;
+            for (uint32_t p = lo - mis + tid; (int32_t)(p - hi) < 0; p += THREADS)
+                if ((int32_t)(p - lo) >= 0) dst[gb + p] = s_keys[p];
+        }
+    } else if (valid == (uint32_t)TILE) {
 #pragma unroll
         for (int i = 0; i < ITEMS; ++i) {
             const uint32_t p = i * THREADS + tid;
@@ -323,11 +386,11 @@ onesweep_lpc32_kernel(const PassArgs a)
 #undef LSD_TRACE
 }
 
-template <int RB, int WARPS, int ITEMS, int MINB, int SHIFT, int LB>
+template <int RB, int WARPS, int ITEMS, int MINB, int SHIFT, int LB, int CLR, bool PEER>
 int onesweep_lpc32_launch_shift(const PassArgs& a, cudaStream_t s)
 {
     using S_ = Lpc32Shape<RB, WARPS, ITEMS>;
-    auto kern = onesweep_lpc32_kernel<RB, WARPS, ITEMS, MINB, SHIFT, LB>;
+    auto kern = onesweep_lpc32_kernel<RB, WARPS, ITEMS, MINB, SHIFT, LB, CLR, PEER>;
     LSD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S_::SMEM_BYTES));
     LSD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     kern<<<a.tiles, S_::THREADS, S_::SMEM_BYTES, s>>>(a);
@@ -335,27 +398,32 @@ int onesweep_lpc32_launch_shift(const PassArgs& a, cudaStream_t s)
     return LSD_OK;
 }
 
-template <int RB, int WARPS, int ITEMS, int MINB, int LB>
+template <int RB, int WARPS, int ITEMS, int MINB, int LB, int CLR, bool PEER>
 int onesweep_lpc32_launch(const PassArgs& a, cudaStream_t s)
 {
     static_assert(RB == 8, "shift dispatch below is written for 8-bit digits");
     switch (a.shift) {
-        case 0: return onesweep_lpc32_launch_shift<RB, WARPS, ITEMS, MINB, 0, LB>(a, s);
-        case 8: return onesweep_lpc32_launch_shift<RB, WARPS, ITEMS, MINB, 8, LB>(a, s);
-        case 16: return onesweep_lpc32_launch_shift<RB, WARPS, ITEMS, MINB, 16, LB>(a, s);
-        case 24: return onesweep_lpc32_launch_shift<RB, WARPS, ITEMS, MINB, 24, LB>(a, s);
+        case 0: return onesweep_lpc32_launch_shift<RB, WARPS, ITEMS, MINB, 0, LB, CLR, PEER>(a, s);
+        case 8: return onesweep_lpc32_launch_shift<RB, WARPS, ITEMS, MINB, 8, LB, CLR, PEER>(a, s);
+        case 16: return onesweep_lpc32_launch_shift<RB, WARPS, ITEMS, MINB, 16, LB, CLR, PEER>(a, s);
+        case 24: return onesweep_lpc32_launch_shift<RB, WARPS, ITEMS, MINB, 24, LB, CLR, PEER>(a, s);
     }
     return LSD_ERR_INVALID_VALUE;
 }
 
 constexpr int kModeLpc32 = 4;
 
-template <int RB, int WARPS, int ITEMS, int MINB, int LB = 8>
+template <int RB, int WARPS, int ITEMS, int MINB, int LB = 8, int CLR = 0, bool WITH_PEER = false>
 constexpr OnesweepLauncher make_lpc32_launcher()
 {
     using S_ = Lpc32Shape<RB, WARPS, ITEMS>;
-    return OnesweepLauncher{RB, S_::THREADS, ITEMS, kModeLpc32, (uint32_t)S_::TILE, S_::PORTION_MAX, S_::SMEM_BYTES,
-                            &onesweep_lpc32_launch<RB, WARPS, ITEMS, MINB, LB>};
+    if constexpr (WITH_PEER)
+        return OnesweepLauncher{RB, S_::THREADS, ITEMS, kModeLpc32, (uint32_t)S_::TILE, S_::PORTION_MAX, S_::SMEM_BYTES,
+                                &onesweep_lpc32_launch<RB, WARPS, ITEMS, MINB, LB, CLR, false>,
+                                &onesweep_lpc32_launch<RB, WARPS, ITEMS, MINB, LB, CLR, true>};
+    else
+        return OnesweepLauncher{RB, S_::THREADS, ITEMS, kModeLpc32, (uint32_t)S_::TILE, S_::PORTION_MAX, S_::SMEM_BYTES,
+                                &onesweep_lpc32_launch<RB, WARPS, ITEMS, MINB, LB, CLR, false>, nullptr};
 }
 
 }  // namespace lsd

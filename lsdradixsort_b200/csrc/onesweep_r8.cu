@@ -9,7 +9,7 @@
 namespace lsd {
 
 static const OnesweepLauncher kTable[] = {
-    make_lpc32_launcher<8, 9, 29, 3, 4>(),       // 0: default -- LPC ranking, 32-bit byte-offset counters, look-back window 4 (= variant 30)
+    make_lpc32_launcher<8, 9, 29, 3, 4, 0, true>(),  // 0: default -- LPC ranking, 32-bit byte-offset counters, look-back window 4 (= variant 30)
     make_launcher<8, 128, 24, kMatchBallot>(),   // 1
     make_launcher<8, 256, 24, kMatchBallot>(),   // 2
     make_launcher<8, 1024, 8, kMatchBallot>(),   // 3
@@ -57,6 +57,7 @@ static const OnesweepLauncher kTable[] = {
     make_cpcp_launcher<8, 64, 4, 8, 0>(),        // 45: same without register reallocation
     make_cpcp_launcher<8, 64, 4, 4, 152>(),      // 46: look-back window 4
     make_cpcp_launcher<8, 48, 5, 8, 0>(),        // 47: tile 6144, 5 buffers, no register reallocation
+    make_lpc32_launcher<8, 9, 29, 3, 4, 1>(),    // 48: as 0 with the matrix zero-filled by st.bulk
 };
 
 const OnesweepLauncher* onesweep_table_r8(int* count)

@@ -195,6 +195,8 @@ int sort_enqueue(uint32_t* keys, uint32_t* scratch, uint64_t n, int r, int block
             a.shift = p * r;
             a.trace = (opt && opt->debug_trace && p == L.passes - 1 && q == 0)
                           ? reinterpret_cast<unsigned long long*>(opt->debug_trace) : nullptr;
+            a.dst_ptrs = nullptr;
+            a.dst_seg = nullptr;
             rc = L.k->launch(a, s);
             if (rc != LSD_OK) return rc;
             ++nl;
@@ -219,7 +221,7 @@ int sort_enqueue(uint32_t* keys, uint32_t* scratch, uint64_t n, int r, int block
 // -------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kPlanThreads)
 single_pass_plan_kernel(const uint64_t* __restrict__ hist, uint64_t* __restrict__ bases, SortPlan* __restrict__ plan,
-                        uint64_t* __restrict__ hist_out, int pass, int H)
+                        uint64_t* __restrict__ hist_out, int pass, int H, int zero_bases)
 {
     __shared__ uint64_t s_warp[kPlanThreads / 32];
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
@@ -235,7 +237,8 @@ single_pass_plan_kernel(const uint64_t* __restrict__ hist, uint64_t* __restrict_
     uint64_t prefix = 0;
     for (uint32_t w = 0; w < warp; ++w) prefix += s_warp[w];
     if ((int)tid < H) {
-        bases[(size_t)(2 * pass) * H + tid] = prefix + incl - v;
+        // peer-scatter mode: every bucket has its own destination pointer, offsets start at 0
+        bases[(size_t)(2 * pass) * H + tid] = zero_bases ? 0ull : prefix + incl - v;
         if (hist_out) hist_out[tid] = prefix + incl - v;
     }
     if (tid == 0) {
@@ -245,19 +248,21 @@ single_pass_plan_kernel(const uint64_t* __restrict__ hist, uint64_t* __restrict_
 }
 
 int pass_enqueue(const uint32_t* in, uint32_t* out, uint64_t n, int r, int bit_group, int block, void* ws,
-                 size_t ws_bytes, uint64_t* hist_out, cudaStream_t s)
+                 size_t ws_bytes, uint64_t* hist_out, cudaStream_t s, const uint64_t* dst_ptrs, const uint32_t* dst_seg)
 {
     SortLayout L;
     const int st = make_layout(n, r, block, nullptr, &L);
     if (st != LSD_OK) return st;
     if (bit_group < 0 || bit_group >= L.passes) return LSD_ERR_INVALID_VALUE;
+    const bool peer = dst_ptrs != nullptr;
+    if (peer && !L.k->launch_peer) return LSD_ERR_UNSUPPORTED;
     if (n == 0) {
         if (hist_out) LSD_CUDA_TRY(cudaMemsetAsync(hist_out, 0, sizeof(uint64_t) * L.H, s));
         return LSD_OK;
     }
-    if (!in || !out || !ws) return LSD_ERR_INVALID_VALUE;
+    if (!in || (!out && !peer) || !ws) return LSD_ERR_INVALID_VALUE;
     if (ws_bytes < L.total_bytes) return LSD_ERR_WORKSPACE_TOO_SMALL;
-    if (!aligned_to(in, 16) || !aligned_to(out, 16) || !aligned_to(ws, 256)) return LSD_ERR_ALIGNMENT;
+    if (!aligned_to(in, 16) || (!peer && !aligned_to(out, 16)) || !aligned_to(ws, 256)) return LSD_ERR_ALIGNMENT;
 
     char* w = static_cast<char*>(ws);
     SortPlan* plan = reinterpret_cast<SortPlan*>(w + L.off_plan);
@@ -268,9 +273,12 @@ int pass_enqueue(const uint32_t* in, uint32_t* out, uint64_t n, int r, int bit_g
     // only this pass's slice of tickets / look-back words is used, but zeroing up to its end is simplest
     const size_t lb_words_per_pass = (size_t)L.total_tiles * L.H;
     LSD_CUDA_TRY(cudaMemsetAsync(ws, 0, L.off_lookback + sizeof(uint32_t) * lb_words_per_pass, s));
-    int rc = launch_digit_histograms(in, n, r, hist, s);
-    if (rc != LSD_OK) return rc;
-    single_pass_plan_kernel<<<1, kPlanThreads, 0, s>>>(hist, bases, plan, hist_out, bit_group, L.H);
+    int rc = LSD_OK;
+    if (!peer) {  // peer-scatter offsets start at 0 in every destination: no global histogram needed
+        rc = launch_digit_histograms(in, n, r, hist, s);
+        if (rc != LSD_OK) return rc;
+    }
+    single_pass_plan_kernel<<<1, kPlanThreads, 0, s>>>(hist, bases, plan, peer ? nullptr : hist_out, bit_group, L.H, peer ? 1 : 0);
     LSD_LAUNCH_CHECK();
     uint32_t* lb = lookback;
     for (uint64_t q = 0; q < L.portions; ++q) {
@@ -290,7 +298,9 @@ int pass_enqueue(const uint32_t* in, uint32_t* out, uint64_t n, int r, int bit_g
         a.pass = bit_group;
         a.shift = bit_group * r;
         a.trace = nullptr;
-        rc = L.k->launch(a, s);
+        a.dst_ptrs = dst_ptrs;
+        a.dst_seg = dst_seg;
+        rc = peer ? L.k->launch_peer(a, s) : L.k->launch(a, s);
         if (rc != LSD_OK) return rc;
         lb += (size_t)a.tiles * L.H;
     }

@@ -86,7 +86,7 @@ def test_sort_skip_disabled_gives_same_result():
 
 
 @pytest.mark.parametrize("kind", ["uniform", "entropy4_table", "all_equal"])
-@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21, 22, 23, 24, 25, 26, 27, 28, 29, 30, 31, 32, 33, 34, 35, 36, 38, 44, 45, 46, 47])
+@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21, 22, 23, 24, 25, 26, 27, 28, 29, 30, 31, 32, 33, 34, 35, 36, 38, 44, 45, 46, 47, 48])
 def test_sort_kernel_variants_r8(variant, kind):
     n = 300_000 + 11
     keys = keygen.make_keys(kind, n, seed=variant)
@@ -365,3 +365,42 @@ def test_build_histogram_matches_reference_gpu(r, block):
     assert ref.ref_device_synchronize() == 0
     ours = L.build_histogram(a, r, 1 if r == 8 else 3, block)
     assert torch.equal(ours.view(-1), h)
+
+
+@pytest.mark.parametrize("n", [1, 1000, 8352, 300_017])
+def test_sort_pass_scatter_with_local_pointers_equals_sort_pass(n):
+    """lsd_sort_pass_scatter (the fused partition + exchange step) with every bucket pointer aimed at one local buffer
+    must reproduce lsd_sort_pass: bucket d at its start offset, stable inside the bucket."""
+    keys = keygen.make_keys("uniform" if n != 1000 else "entropy4_table", n, seed=n)
+    src = dev(keys)
+    want = torch.empty_like(src)
+    L.sort_pass(src, want, 8, 3)
+    starts = np.concatenate([[0], np.cumsum(np.bincount(keys >> 24, minlength=256))[:-1]]).astype(np.int64)
+    out = torch.full((n + 8,), -1, dtype=torch.int32, device="cuda")
+    ptrs = torch.from_numpy(out.data_ptr() + 4 * starts).cuda()
+    L.sort_pass_scatter(src, ptrs, 8, 3)
+    torch.cuda.synchronize()
+    assert np.array_equal(host(out[:n]), host(want))
+    assert bool((out[n:] == -1).all())
+    ref_out = np.zeros(n, dtype=np.uint32)
+    _oracle.oracle().lsd_oracle_sort_pass(keys.copy(), ref_out, n, np.zeros(256, dtype=np.uint32), 8, 3)
+    assert np.array_equal(host(out[:n]), ref_out)
+
+
+def test_sort_pass_scatter_segments_group_buckets_per_tile():
+    """Two destination segments (buckets 0..127 and 128..255): each destination receives exactly its keys, and sorting
+    what arrived gives the same multiset as the oracle (the order inside a destination is (tile, bucket, position))."""
+    n = 100_000
+    keys = keygen.make_keys("uniform", n, seed=5)
+    src = dev(keys)
+    lo_cnt = int((keys >> 24 < 128).sum())
+    a = torch.full((lo_cnt + 4,), -1, dtype=torch.int32, device="cuda")
+    b = torch.full((n - lo_cnt + 4,), -1, dtype=torch.int32, device="cuda")
+    ptrs = torch.tensor([a.data_ptr()] * 128 + [b.data_ptr()] * 128, dtype=torch.int64).cuda()
+    seg = torch.tensor([0 | (127 << 16)] * 128 + [128 | (255 << 16)] * 128, dtype=torch.int32).cuda()
+    L.sort_pass_scatter(src, ptrs, 8, 3, dst_seg=seg)
+    torch.cuda.synchronize()
+    assert bool((a[lo_cnt:] == -1).all()) and bool((b[n - lo_cnt:] == -1).all())
+    ga, gb = host(a[:lo_cnt]), host(b[: n - lo_cnt])
+    assert np.array_equal(np.sort(ga), np.sort(keys[keys >> 24 < 128]))
+    assert np.array_equal(np.sort(gb), np.sort(keys[keys >> 24 >= 128]))

@@ -56,6 +56,36 @@ def test_split_sizes_conserve_keys():
             assert mat[s][0][d] == mat[d][1][s]  # what s sends to d is what d expects from s
 
 
+def test_scatter_destinations_partition_every_receive_buffer():
+    """Fused partition+exchange: the blocks the sources write into one receive buffer tile it exactly (no gap, no
+    overlap), in source-rank order, with the split sizes all_to_all_single would use; segments are owner runs."""
+    rng = np.random.default_rng(7)
+    world, n_local = 3, 4000
+    keys = [rng.integers(0, 2**32, n_local, dtype=np.uint64).astype(np.uint32) for _ in range(world)]
+    keys[1][:1500] = 0x7F000001  # a heavy bucket
+    per_rank = np.stack([np.bincount(k >> 24, minlength=256) for k in keys]).astype(np.int64)
+    owner = multi.assign_buckets(per_rank.sum(axis=0), world)
+    got = [[] for _ in range(world)]
+    for s in range(world):
+        dest_rank, dest_off, seg = multi.scatter_destinations(per_rank, owner, s)
+        ins, _ = multi.split_sizes(per_rank, owner, s)
+        assert np.array_equal(dest_rank, owner)
+        for o in range(world):
+            idx = np.nonzero(owner == o)[0]
+            if idx.size == 0:
+                continue
+            assert len(set(dest_off[idx].tolist())) == 1  # one block per (source, destination)
+            assert all(int(v) == (int(idx[0]) | (int(idx[-1]) << 16)) for v in seg[idx])
+            got[o].append((int(dest_off[idx[0]]), ins[o], s))
+    for o in range(world):
+        _, outs = multi.split_sizes(per_rank, owner, o)
+        pos = 0
+        for off, size, s in sorted(got[o]):
+            assert off == pos and size == outs[s]
+            pos += size
+        assert pos == sum(outs)
+
+
 class OracleOps:
     """Test double for multi.CudaOps: same interface, CPU tensors, oracle arithmetic."""
 
