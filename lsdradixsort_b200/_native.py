@@ -13,7 +13,7 @@ from pathlib import Path
 
 PKG_DIR = Path(__file__).resolve().parent
 REPO_ROOT = PKG_DIR.parent
-LIB_PATH = PKG_DIR / "liblsdsort.so"
+LIB_PATH = Path(os.environ["LSDSORT_LIB"]) if os.environ.get("LSDSORT_LIB") else PKG_DIR / "liblsdsort.so"  # override: tuning builds
 
 LSD_OK = 0
 LSD_ERR_INVALID_VALUE = 1

@@ -60,7 +60,7 @@ __device__ __forceinline__ uint32_t cell_offset(uint32_t key, uint32_t lane4)
     return (x & mask) | lane4;
 }
 
-template <int RB, int WARPS, int ITEMS, int MINB, int SHIFT, int LB, int CLR, bool PEER>
+template <int RB, int WARPS, int ITEMS, int MINB, int SHIFT, int LB, int CLR, bool PEER, bool SP>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
 onesweep_lpc32_kernel(const PassArgs a)
 {
@@ -174,7 +174,60 @@ onesweep_lpc32_kernel(const PassArgs a)
 
     uint32_t* lb_row = a.lookback + (size_t)tile * H;
 
-    if (warp < (uint32_t)SW) {
+    if constexpr (SP) {
+        // ================= single-pass scan: warps 0..7, one matrix row per thread, the row stays in registers
+        // between the totals and the prefix write (one 128-bit read pass less: ~1 wavefront per 32 keys) =============
+        static_assert(!SP || (H == 256 && WARPS >= 9), "single-pass scan: 256 rows over 8 warps, look-back by the last 4");
+        const uint32_t q = lane & 7u;
+        const uint32_t row = warp * 32u + lane;
+        uint4 v[8];
+        uint32_t total = 0, below = 0, start = 0;
+        if (warp < 8u) {
+            const uint4* r4 = reinterpret_cast<const uint4*>(s_mat + row * 32u);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const uint32_t grp = (q + k) & 7u;
+                v[k] = r4[grp];
+                const uint32_t sum = v[k].x + v[k].y + v[k].z + v[k].w;
+                total += sum;
+                if (grp < q) below += sum;
+            }
+            uint32_t incl = total;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(kFullMask, incl, o);
+                if (lane >= (uint32_t)o) incl += t;
+            }
+            start = incl - total;
+            if (lane == 31) s_misc[warp] = incl;
+            s_tot[row] = total >> 2;
+        }
+        __syncthreads();  // totals visible
+        if (warp < 8u) {
+            uint32_t prefix = 0;
+#pragma unroll
+            for (int w = 0; w < 8; ++w)
+                if ((uint32_t)w < warp) prefix += s_misc[w];
+            start += prefix;
+            s_dp[row] = start >> 2;
+            uint4* r4 = reinterpret_cast<uint4*>(s_mat + row * 32u);
+            uint32_t run = start + below;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const uint32_t grp = (q + k) & 7u;
+                if (grp == 0) run = start;
+                uint4 o;
+                o.x = run; run += v[k].x;
+                o.y = run; run += v[k].y;
+                o.z = run; run += v[k].z;
+                o.w = run; run += v[k].w;
+                r4[grp] = o;
+            }
+        }
+        __syncthreads();  // matrix, totals and bucket starts complete
+        if (warp == 0) LSD_TRACE(5);
+    }
+    if (!SP && warp < (uint32_t)SW) {
         // ================= scan warps: totals -> bucket starts -> exclusive lane prefix =================
         const uint32_t q = lane & 7u;
         uint32_t total[GPW], below[GPW];
@@ -257,7 +310,7 @@ onesweep_lpc32_kernel(const PassArgs a)
         if (warp == 0) LSD_TRACE(5);  // scan pass 2 done: rank chain opens
     } else if (warp >= (uint32_t)(WARPS - LBW)) {
         // ================= look-back warps (tail of the rank chain): one digit pair per thread =================
-        named_bar_sync(kBarTot, (SW + LBW) * 32);
+        if constexpr (!SP) named_bar_sync(kBarTot, (SW + LBW) * 32);
         if (warp == (uint32_t)WARPS - 1) LSD_TRACE(8);  // look-back starts
         const uint32_t dt = tid - (uint32_t)(THREADS - LBT);
         if (dt < (uint32_t)H / 2) {
@@ -386,11 +439,11 @@ onesweep_lpc32_kernel(const PassArgs a)
 #undef LSD_TRACE
 }
 
-template <int RB, int WARPS, int ITEMS, int MINB, int SHIFT, int LB, int CLR, bool PEER>
+template <int RB, int WARPS, int ITEMS, int MINB, int SHIFT, int LB, int CLR, bool PEER, bool SP>
 int onesweep_lpc32_launch_shift(const PassArgs& a, cudaStream_t s)
 {
     using S_ = Lpc32Shape<RB, WARPS, ITEMS>;
-    auto kern = onesweep_lpc32_kernel<RB, WARPS, ITEMS, MINB, SHIFT, LB, CLR, PEER>;
+    auto kern = onesweep_lpc32_kernel<RB, WARPS, ITEMS, MINB, SHIFT, LB, CLR, PEER, SP>;
     LSD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S_::SMEM_BYTES));
     LSD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     kern<<<a.tiles, S_::THREADS, S_::SMEM_BYTES, s>>>(a);
@@ -398,32 +451,32 @@ int onesweep_lpc32_launch_shift(const PassArgs& a, cudaStream_t s)
     return LSD_OK;
 }
 
-template <int RB, int WARPS, int ITEMS, int MINB, int LB, int CLR, bool PEER>
+template <int RB, int WARPS, int ITEMS, int MINB, int LB, int CLR, bool PEER, bool SP>
 int onesweep_lpc32_launch(const PassArgs& a, cudaStream_t s)
 {
     static_assert(RB == 8, "shift dispatch below is written for 8-bit digits");
     switch (a.shift) {
-        case 0: return onesweep_lpc32_launch_shift<RB, WARPS, ITEMS, MINB, 0, LB, CLR, PEER>(a, s);
-        case 8: return onesweep_lpc32_launch_shift<RB, WARPS, ITEMS, MINB, 8, LB, CLR, PEER>(a, s);
-        case 16: return onesweep_lpc32_launch_shift<RB, WARPS, ITEMS, MINB, 16, LB, CLR, PEER>(a, s);
-        case 24: return onesweep_lpc32_launch_shift<RB, WARPS, ITEMS, MINB, 24, LB, CLR, PEER>(a, s);
+        case 0: return onesweep_lpc32_launch_shift<RB, WARPS, ITEMS, MINB, 0, LB, CLR, PEER, SP>(a, s);
+        case 8: return onesweep_lpc32_launch_shift<RB, WARPS, ITEMS, MINB, 8, LB, CLR, PEER, SP>(a, s);
+        case 16: return onesweep_lpc32_launch_shift<RB, WARPS, ITEMS, MINB, 16, LB, CLR, PEER, SP>(a, s);
+        case 24: return onesweep_lpc32_launch_shift<RB, WARPS, ITEMS, MINB, 24, LB, CLR, PEER, SP>(a, s);
     }
     return LSD_ERR_INVALID_VALUE;
 }
 
 constexpr int kModeLpc32 = 4;
 
-template <int RB, int WARPS, int ITEMS, int MINB, int LB = 8, int CLR = 0, bool WITH_PEER = false>
+template <int RB, int WARPS, int ITEMS, int MINB, int LB = 8, int CLR = 0, bool WITH_PEER = false, bool SP = false>
 constexpr OnesweepLauncher make_lpc32_launcher()
 {
     using S_ = Lpc32Shape<RB, WARPS, ITEMS>;
     if constexpr (WITH_PEER)
         return OnesweepLauncher{RB, S_::THREADS, ITEMS, kModeLpc32, (uint32_t)S_::TILE, S_::PORTION_MAX, S_::SMEM_BYTES,
-                                &onesweep_lpc32_launch<RB, WARPS, ITEMS, MINB, LB, CLR, false>,
-                                &onesweep_lpc32_launch<RB, WARPS, ITEMS, MINB, LB, CLR, true>};
+                                &onesweep_lpc32_launch<RB, WARPS, ITEMS, MINB, LB, CLR, false, SP>,
+                                &onesweep_lpc32_launch<RB, WARPS, ITEMS, MINB, LB, CLR, true, SP>};
     else
         return OnesweepLauncher{RB, S_::THREADS, ITEMS, kModeLpc32, (uint32_t)S_::TILE, S_::PORTION_MAX, S_::SMEM_BYTES,
-                                &onesweep_lpc32_launch<RB, WARPS, ITEMS, MINB, LB, CLR, false>, nullptr};
+                                &onesweep_lpc32_launch<RB, WARPS, ITEMS, MINB, LB, CLR, false, SP>, nullptr};
 }
 
 }  // namespace lsd

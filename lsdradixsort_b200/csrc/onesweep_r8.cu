@@ -58,6 +58,9 @@ static const OnesweepLauncher kTable[] = {
     make_cpcp_launcher<8, 64, 4, 4, 152>(),      // 46: look-back window 4
     make_cpcp_launcher<8, 48, 5, 8, 0>(),        // 47: tile 6144, 5 buffers, no register reallocation
     make_lpc32_launcher<8, 9, 29, 3, 4, 1>(),    // 48: as 0 with the matrix zero-filled by st.bulk
+    make_lpc32_launcher<8, 9, 29, 3, 4, 0, false, true>(),   // 49: single-pass matrix scan (rows kept in registers)
+    make_lpc32_launcher<8, 9, 29, 3, 8, 0, false, true>(),   // 50: same, look-back window 8
+    make_lpc32_launcher<8, 9, 31, 3, 4, 0, false, true>(),   // 51: single-pass scan, tile 8928
 };
 
 const OnesweepLauncher* onesweep_table_r8(int* count)

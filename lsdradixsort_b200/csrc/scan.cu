@@ -14,6 +14,8 @@
 // block scheduling order).  Tile state is one 64-bit word {flag:32 | value:32}: flag 1 = tile
 // aggregate, flag 2 = inclusive prefix; flag and value travel in one relaxed store, so no fence
 // is needed.  Warp 0 looks back 32 predecessors at a time.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace lsd {
@@ -169,6 +171,173 @@ scan_kernel(uint32_t* __restrict__ a, uint64_t n, ScanWorkspace* __restrict__ ws
     }
 }
 
+// -------------------------------------------------------------------------------------
+// scan_tma_kernel: the same single-pass scan, tile staged in shared memory by one TMA bulk copy.
+//
+// Why (ncu, profiles/r01_scan_ncu.txt): scan_kernel keeps its 32 elements per thread in registers while
+// warp 0 walks the look-back chain -- 64 registers x 256 threads -> 4 CTAs per SM, 53 % of all stall samples on
+// the barrier behind the look-back, 3.5 TB/s.  Here the tile lands in shared memory (16 KiB per 128-thread CTA),
+// the threads only keep 8 running sums across the wait (~40 registers), and re-read their vectors from shared
+// memory once the tile prefix is known: 12-13 CTAs per SM are in flight, which is what the HBM latency x bandwidth
+// product of B200 needs.
+// -------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t scan_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ uint4 lds128_volatile(const uint32_t* p)
+{
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(scan_smem_u32(p)));
+    return v;
+}
+
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS)
+scan_tma_kernel(uint32_t* __restrict__ a, uint64_t n, ScanWorkspace* __restrict__ ws, uint32_t* __restrict__ trace)
+{
+    const long long t_start = trace ? clock64() : 0;
+#define SCAN_TRACE(slot) do { if (trace && tid == 0) trace[(size_t)tile * 8 + (slot)] = (uint32_t)(clock64() - t_start); } while (0)
+    constexpr int WARPS = THREADS / 32;
+    constexpr int TILE = THREADS * kScanItems;
+    constexpr int P = kScanVecs * WARPS;
+    constexpr int PPL = P / 32;
+    static_assert(P % 32 == 0 && PPL >= 1, "partials must fill warp 0 evenly");
+
+    extern __shared__ __align__(128) uint32_t s_data[];  // [TILE]
+    __shared__ __align__(8) uint64_t s_bar;
+    __shared__ uint32_t s_tile;
+    __shared__ uint32_t s_partial[kScanVecs * WARPS];
+    __shared__ uint32_t s_tile_prefix;
+
+    const uint32_t tid = threadIdx.x;
+    const uint32_t lane = tid & 31u;
+    const uint32_t warp = tid >> 5;
+
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(scan_smem_u32(&s_bar)) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        const uint32_t t = atomicAdd(&ws->ticket, 1u);
+        s_tile = t;
+        if (trace) trace[(size_t)t * 8 + 0] = (uint32_t)(clock64() - t_start);
+        const uint64_t b = (uint64_t)t * TILE;
+        if (n - b >= (uint64_t)TILE) {
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(scan_smem_u32(&s_bar)), "r"(TILE * 4) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(scan_smem_u32(s_data)), "l"(a + b), "r"(TILE * 4), "r"(scan_smem_u32(&s_bar)) : "memory");
+        }
+    }
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const uint64_t base = (uint64_t)tile * TILE;
+    const uint64_t left = n - base;
+    const bool full = left >= (uint64_t)TILE;
+    if (full) {
+        asm volatile(
+            "{\n.reg .pred p;\nSCAN_WAIT_%=:\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n"
+            "@p bra SCAN_DONE_%=;\nbra SCAN_WAIT_%=;\nSCAN_DONE_%=:\n}\n" ::"r"(scan_smem_u32(&s_bar)) : "memory");
+    } else {
+        for (uint32_t i = tid; i < (uint32_t)TILE; i += THREADS) s_data[i] = i < left ? a[base + i] : 0u;
+        __syncthreads();
+    }
+
+    SCAN_TRACE(1);  // tile landed
+    // ---- per-vector sums, warp scans (only the 8 running sums stay in registers) ----
+    uint32_t excl[kScanVecs];
+#pragma unroll
+    for (int j = 0; j < kScanVecs; ++j) {
+        const uint4 v = lds128_volatile(s_data + 4 * (j * THREADS + tid));
+        const uint32_t sum = v.x + v.y + v.z + v.w;
+        const uint32_t incl = warp_inclusive_scan(sum, lane);
+        excl[j] = incl - sum;
+        if (lane == 31) s_partial[j * WARPS + warp] = incl;
+    }
+    __syncthreads();
+
+    SCAN_TRACE(2);  // partials done
+    if (warp == 0) {
+        uint32_t part[PPL];
+        uint32_t lane_sum = 0;
+#pragma unroll
+        for (int k = 0; k < PPL; ++k) {
+            part[k] = s_partial[lane * PPL + k];
+            lane_sum += part[k];
+        }
+        const uint32_t lane_incl = warp_inclusive_scan(lane_sum, lane);
+        const uint32_t tile_total = __shfl_sync(kFullMask, lane_incl, 31);
+        uint32_t run = lane_incl - lane_sum;
+#pragma unroll
+        for (int k = 0; k < PPL; ++k) {
+            s_partial[lane * PPL + k] = run;
+            run += part[k];
+        }
+        // ---- decoupled look-back, 32 predecessors per round trip ----
+        // Tried and measured slower on B200 (profiles/r01_scan_variants.txt): 64/128/256-wide windows (more strong loads
+        // per round), exponential back-off on failed polls, and span records that let walkers skip what a predecessor
+        // has already summed.  With ~900 tiles in flight the walk is ~18 rounds; what helped was taking the tile out of
+        // the registers (this kernel) so that more tiles are in flight per SM.
+        uint32_t exclusive = 0;
+        if (tile == 0) {
+            if (lane == 0) st_relaxed_gpu(&ws->state[0], kFlagInclusive | tile_total);
+        } else {
+            if (lane == 0) st_relaxed_gpu(&ws->state[tile], kFlagAggregate | tile_total);
+            int64_t look = (int64_t)tile - 1;
+            while (true) {
+                const int64_t idx = look - (int64_t)lane;
+                const uint64_t w = idx >= 0 ? ld_relaxed_gpu(&ws->state[idx]) : kFlagInclusive;  // virtual tiles: prefix 0
+                const uint32_t ready = __ballot_sync(kFullMask, (w >> 32) != 0);
+                const uint32_t incl_mask = __ballot_sync(kFullMask, (w >> 32) == 2);
+                uint32_t take = (uint32_t)w;
+                bool finished = false;
+                if (incl_mask) {
+                    const uint32_t first = __ffs(incl_mask) - 1;
+                    const uint32_t need = (2u << first) - 1u;
+                    if ((ready & need) != need) continue;
+                    if (lane > first) take = 0;
+                    finished = true;
+                } else if (ready != kFullMask) {
+                    continue;
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) take += __shfl_xor_sync(kFullMask, take, o);
+                exclusive += take;
+                if (finished) break;
+                look -= 32;
+            }
+            if (lane == 0) st_relaxed_gpu(&ws->state[tile], kFlagInclusive | (uint32_t)(exclusive + tile_total));
+        }
+        if (lane == 0) s_tile_prefix = exclusive;
+    }
+    __syncthreads();
+
+    SCAN_TRACE(3);  // look-back done
+    // ---- re-read the vectors from shared memory, exclusive results, streaming stores ----
+    const uint32_t tile_prefix = s_tile_prefix;
+#pragma unroll
+    for (int j = 0; j < kScanVecs; ++j) {
+        const uint4 v = lds128_volatile(s_data + 4 * (j * THREADS + tid));
+        uint32_t run = tile_prefix + s_partial[j * WARPS + warp] + excl[j];
+        uint4 o;
+        o.x = run; run += v.x;
+        o.y = run; run += v.y;
+        o.z = run; run += v.z;
+        o.w = run;
+        const uint64_t e = 4ull * (j * THREADS + tid);
+        if (full) {
+            __stcs(reinterpret_cast<uint4*>(a + base + e), o);
+        } else {
+            if (e + 0 < left) a[base + e + 0] = o.x;
+            if (e + 1 < left) a[base + e + 1] = o.y;
+            if (e + 2 < left) a[base + e + 2] = o.z;
+            if (e + 3 < left) a[base + e + 3] = o.w;
+        }
+    }
+    SCAN_TRACE(4);  // stores issued
+#undef SCAN_TRACE
+}
+
+// LSD_SCAN_REGISTER_PATH=1 selects the register-resident kernel (tuning comparisons); unaligned arrays use it too.
+static const bool g_scan_register_path = [] { const char* e = getenv("LSD_SCAN_REGISTER_PATH"); return e && e[0] == '1'; }();
+
 static int scan_threads_for(int block)
 {
     if (block <= 0) return 256;
@@ -177,11 +346,14 @@ static int scan_threads_for(int block)
     return 512;
 }
 
+// LSD_SCAN_TRACE=1 (tuning aid): 8 uint32 phase clocks per tile are written after the tile states
+static const bool g_scan_trace = [] { const char* e = getenv("LSD_SCAN_TRACE"); return e && e[0] == '1'; }();
+
 size_t scan_workspace_bytes(uint64_t n, int block)
 {
     const uint64_t tile = (uint64_t)scan_threads_for(block) * kScanItems;
     const uint64_t tiles = (n + tile - 1) / tile;
-    return sizeof(ScanWorkspace) + (size_t)(tiles ? tiles : 1) * sizeof(uint64_t);
+    return sizeof(ScanWorkspace) + (size_t)(tiles ? tiles : 1) * sizeof(uint64_t) * (g_scan_trace ? 5 : 1);
 }
 
 int launch_prefix_sum(uint32_t* a, uint64_t n, int block, void* ws, size_t ws_bytes, cudaStream_t s)
@@ -195,10 +367,30 @@ int launch_prefix_sum(uint32_t* a, uint64_t n, int block, void* ws, size_t ws_by
     if (tiles > 0x7FFFFFFFull) return LSD_ERR_UNSUPPORTED;
     LSD_CUDA_TRY(cudaMemsetAsync(ws, 0, need, s));
     auto* w = static_cast<ScanWorkspace*>(ws);
-    switch (threads) {
-        case 128: scan_kernel<128><<<(unsigned)tiles, 128, 0, s>>>(a, n, w); break;
-        case 256: scan_kernel<256><<<(unsigned)tiles, 256, 0, s>>>(a, n, w); break;
-        default: scan_kernel<512><<<(unsigned)tiles, 512, 0, s>>>(a, n, w); break;
+    const bool tma = !g_scan_register_path && aligned_to(a, 16);
+    uint32_t* trace = g_scan_trace ? reinterpret_cast<uint32_t*>(w->state + tiles) : nullptr;
+    const size_t smem = (size_t)threads * kScanItems * sizeof(uint32_t);
+    if (tma) {
+        switch (threads) {
+            case 128:
+                LSD_CUDA_TRY(cudaFuncSetAttribute(scan_tma_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                scan_tma_kernel<128><<<(unsigned)tiles, 128, smem, s>>>(a, n, w, trace);
+                break;
+            case 256:
+                LSD_CUDA_TRY(cudaFuncSetAttribute(scan_tma_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                scan_tma_kernel<256><<<(unsigned)tiles, 256, smem, s>>>(a, n, w, trace);
+                break;
+            default:
+                LSD_CUDA_TRY(cudaFuncSetAttribute(scan_tma_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                scan_tma_kernel<512><<<(unsigned)tiles, 512, smem, s>>>(a, n, w, trace);
+                break;
+        }
+    } else {
+        switch (threads) {
+            case 128: scan_kernel<128><<<(unsigned)tiles, 128, 0, s>>>(a, n, w); break;
+            case 256: scan_kernel<256><<<(unsigned)tiles, 256, 0, s>>>(a, n, w); break;
+            default: scan_kernel<512><<<(unsigned)tiles, 512, 0, s>>>(a, n, w); break;
+        }
     }
     LSD_LAUNCH_CHECK();
     return LSD_OK;
