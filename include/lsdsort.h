@@ -79,6 +79,9 @@ LSD_API int lsd_build_histogram(const uint32_t *keys, uint64_t n, int r, int bit
  * the column sum of build_histogram over all tiles for every bit group (what the reference
  * recomputes per pass at :850), hoisted out of the pass loop. */
 LSD_API int lsd_digit_histograms(const uint32_t *keys, uint64_t n, int r, uint64_t *hist, lsd_stream_t stream);
+/* Same layout ([32/r][2^r] uint64, overwritten) but only the TOP digit's row is counted, the others are zero: one
+ * shared-memory atomic per key instead of 32/r.  The planning step of the multi-GPU sort (bucket -> rank map). */
+LSD_API int lsd_top_digit_histogram(const uint32_t *keys, uint64_t n, int r, uint64_t *hist, lsd_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------
  * prefix_sum

@@ -23,6 +23,7 @@ from .api import (  # noqa: F401
     sort_pass,
     sort_pass_scatter,
     sort_workspace_bytes,
+    top_digit_histogram,
 )
 
 __version__ = "0.1.0"

@@ -74,6 +74,7 @@ def lib() -> C.CDLL:
         "lsd_build_histogram_bytes": (C.c_size_t, [C.c_uint64, C.c_int, C.c_int]),
         "lsd_build_histogram": (C.c_int, [vp, C.c_uint64, C.c_int, C.c_int, C.c_int, vp, vp]),
         "lsd_digit_histograms": (C.c_int, [vp, C.c_uint64, C.c_int, vp, vp]),
+        "lsd_top_digit_histogram": (C.c_int, [vp, C.c_uint64, C.c_int, vp, vp]),
         "lsd_prefix_sum_workspace_bytes": (C.c_size_t, [C.c_uint64, C.c_int]),
         "lsd_prefix_sum": (C.c_int, [vp, C.c_uint64, C.c_int, vp, C.c_size_t, vp]),
         "lsd_sort_workspace_bytes": (C.c_size_t, [C.c_uint64, C.c_int, C.c_int]),

@@ -88,6 +88,17 @@ def digit_histograms(keys: torch.Tensor, r: int = 8) -> torch.Tensor:
     return out
 
 
+def top_digit_histogram(keys: torch.Tensor, r: int = 8) -> torch.Tensor:
+    """Histogram of the most significant digit only: ``[2^r]`` int64 (lsd_top_digit_histogram)."""
+    _check_keys(keys, "keys")
+    out = torch.empty((32 // r, 1 << r), dtype=torch.int64, device=keys.device)
+    N.check(
+        N.lib().lsd_top_digit_histogram(keys.data_ptr(), keys.numel(), r, out.data_ptr(), _stream_ptr(keys.device)),
+        "lsd_top_digit_histogram",
+    )
+    return out[-1]
+
+
 # --------------------------------------------------------------------------------------------------
 # prefix_sum
 # --------------------------------------------------------------------------------------------------

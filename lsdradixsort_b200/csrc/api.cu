@@ -106,6 +106,14 @@ LSD_API int lsd_digit_histograms(const uint32_t* keys, uint64_t n, int r, uint64
     return launch_digit_histograms(keys, n, r, hist, (cudaStream_t)stream);
 }
 
+LSD_API int lsd_top_digit_histogram(const uint32_t* keys, uint64_t n, int r, uint64_t* hist, lsd_stream_t stream)
+{
+    if (!valid_radix(r)) return LSD_ERR_INVALID_VALUE;
+    if (!hist || (n > 0 && !keys)) return LSD_ERR_INVALID_VALUE;
+    if (n > 0 && !aligned_to(keys, 16)) return LSD_ERR_ALIGNMENT;
+    return launch_top_digit_histogram(keys, n, r, hist, (cudaStream_t)stream);
+}
+
 // ---- prefix_sum ----------------------------------------------------------------------
 LSD_API size_t lsd_prefix_sum_workspace_bytes(uint64_t n, int block) { return scan_workspace_bytes(n, block); }
 

@@ -98,6 +98,7 @@ int smem_optin_bytes();  // cached max opt-in shared memory per block
 
 // ---- entry points implemented per translation unit (called by api.cu) ----------------
 int launch_digit_histograms(const uint32_t* keys, uint64_t n, int r, uint64_t* hist, cudaStream_t s);
+int launch_top_digit_histogram(const uint32_t* keys, uint64_t n, int r, uint64_t* hist, cudaStream_t s);
 int launch_tile_histograms(const uint32_t* keys, uint64_t n, int r, int bit_group, int block, uint32_t* hist,
                            cudaStream_t s);
 size_t scan_workspace_bytes(uint64_t n, int block);

@@ -25,19 +25,19 @@ namespace lsd {
 // -------------------------------------------------------------------------------------
 constexpr int kHistThreads = 1024;
 
-template <int RB>
+template <int RB, bool TOP_ONLY = false>
 __device__ __forceinline__ void hist_add_key(uint32_t* cnt_lane, uint32_t key)
 {
     constexpr int NP = 32 / RB;
     constexpr int H = 1 << RB;
 #pragma unroll
-    for (int p = 0; p < NP; ++p) {
+    for (int p = TOP_ONLY ? NP - 1 : 0; p < NP; ++p) {
         const uint32_t d = (key >> (p * RB)) & (H - 1);
         atomicAdd(cnt_lane + ((p * H + d) << 5), 1u);
     }
 }
 
-template <int RB>
+template <int RB, bool TOP_ONLY = false>
 __global__ void __launch_bounds__(kHistThreads, 1)
 digit_hist_kernel(const uint32_t* __restrict__ keys, uint64_t n, unsigned long long* __restrict__ hist)
 {
@@ -62,24 +62,24 @@ digit_hist_kernel(const uint32_t* __restrict__ keys, uint64_t n, unsigned long l
         const uint4 b = ld_stream_v4(keys + 4 * (i + stride));
         const uint4 c = ld_stream_v4(keys + 4 * (i + 2 * stride));
         const uint4 d = ld_stream_v4(keys + 4 * (i + 3 * stride));
-        hist_add_key<RB>(cnt_lane, a.x); hist_add_key<RB>(cnt_lane, a.y);
-        hist_add_key<RB>(cnt_lane, a.z); hist_add_key<RB>(cnt_lane, a.w);
-        hist_add_key<RB>(cnt_lane, b.x); hist_add_key<RB>(cnt_lane, b.y);
-        hist_add_key<RB>(cnt_lane, b.z); hist_add_key<RB>(cnt_lane, b.w);
-        hist_add_key<RB>(cnt_lane, c.x); hist_add_key<RB>(cnt_lane, c.y);
-        hist_add_key<RB>(cnt_lane, c.z); hist_add_key<RB>(cnt_lane, c.w);
-        hist_add_key<RB>(cnt_lane, d.x); hist_add_key<RB>(cnt_lane, d.y);
-        hist_add_key<RB>(cnt_lane, d.z); hist_add_key<RB>(cnt_lane, d.w);
+        hist_add_key<RB, TOP_ONLY>(cnt_lane, a.x); hist_add_key<RB, TOP_ONLY>(cnt_lane, a.y);
+        hist_add_key<RB, TOP_ONLY>(cnt_lane, a.z); hist_add_key<RB, TOP_ONLY>(cnt_lane, a.w);
+        hist_add_key<RB, TOP_ONLY>(cnt_lane, b.x); hist_add_key<RB, TOP_ONLY>(cnt_lane, b.y);
+        hist_add_key<RB, TOP_ONLY>(cnt_lane, b.z); hist_add_key<RB, TOP_ONLY>(cnt_lane, b.w);
+        hist_add_key<RB, TOP_ONLY>(cnt_lane, c.x); hist_add_key<RB, TOP_ONLY>(cnt_lane, c.y);
+        hist_add_key<RB, TOP_ONLY>(cnt_lane, c.z); hist_add_key<RB, TOP_ONLY>(cnt_lane, c.w);
+        hist_add_key<RB, TOP_ONLY>(cnt_lane, d.x); hist_add_key<RB, TOP_ONLY>(cnt_lane, d.y);
+        hist_add_key<RB, TOP_ONLY>(cnt_lane, d.z); hist_add_key<RB, TOP_ONLY>(cnt_lane, d.w);
     }
     for (; i < nvec; i += stride) {
         const uint4 a = ld_stream_v4(keys + 4 * i);
-        hist_add_key<RB>(cnt_lane, a.x); hist_add_key<RB>(cnt_lane, a.y);
-        hist_add_key<RB>(cnt_lane, a.z); hist_add_key<RB>(cnt_lane, a.w);
+        hist_add_key<RB, TOP_ONLY>(cnt_lane, a.x); hist_add_key<RB, TOP_ONLY>(cnt_lane, a.y);
+        hist_add_key<RB, TOP_ONLY>(cnt_lane, a.z); hist_add_key<RB, TOP_ONLY>(cnt_lane, a.w);
     }
     // ragged tail (n % 4 keys) -- block 0 only
     if (blockIdx.x == 0) {
         const uint64_t t = (nvec << 2) + tid;
-        if (t < n) hist_add_key<RB>(cnt_lane, keys[t]);
+        if (t < n) hist_add_key<RB, TOP_ONLY>(cnt_lane, keys[t]);
     }
     __syncthreads();
 
@@ -92,21 +92,34 @@ digit_hist_kernel(const uint32_t* __restrict__ keys, uint64_t n, unsigned long l
     }
 }
 
-template <int RB>
+template <int RB, bool TOP_ONLY = false>
 static int launch_digit_hist_t(const uint32_t* keys, uint64_t n, uint64_t* hist, cudaStream_t s)
 {
     constexpr int ROWS = (32 / RB) << RB;
     const size_t smem = (size_t)ROWS * 32 * sizeof(uint32_t);
     LSD_CUDA_TRY(cudaMemsetAsync(hist, 0, (size_t)ROWS * sizeof(uint64_t), s));
     if (n == 0) return LSD_OK;
-    LSD_CUDA_TRY(cudaFuncSetAttribute(digit_hist_kernel<RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    LSD_CUDA_TRY(cudaFuncSetAttribute(digit_hist_kernel<RB, TOP_ONLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // one CTA per SM, but never more CTAs than there are 16 KiB slices of input
     const uint64_t slices = ((n >> 2) + kHistThreads - 1) / kHistThreads;
     int grid = sm_count();
     if ((uint64_t)grid > slices) grid = (int)(slices ? slices : 1);
-    digit_hist_kernel<RB><<<grid, kHistThreads, smem, s>>>(keys, n, reinterpret_cast<unsigned long long*>(hist));
+    digit_hist_kernel<RB, TOP_ONLY><<<grid, kHistThreads, smem, s>>>(keys, n, reinterpret_cast<unsigned long long*>(hist));
     LSD_LAUNCH_CHECK();
     return LSD_OK;
+}
+
+// Top digit only (one shared atomic per key instead of 32/r): the multi-GPU planning step.  Same [32/r][2^r] layout,
+// the other rows are zero.
+int launch_top_digit_histogram(const uint32_t* keys, uint64_t n, int r, uint64_t* hist, cudaStream_t s)
+{
+    switch (r) {
+        case 1: return launch_digit_hist_t<1, true>(keys, n, hist, s);
+        case 2: return launch_digit_hist_t<2, true>(keys, n, hist, s);
+        case 4: return launch_digit_hist_t<4, true>(keys, n, hist, s);
+        case 8: return launch_digit_hist_t<8, true>(keys, n, hist, s);
+    }
+    return LSD_ERR_INVALID_VALUE;
 }
 
 int launch_digit_histograms(const uint32_t* keys, uint64_t n, int r, uint64_t* hist, cudaStream_t s)

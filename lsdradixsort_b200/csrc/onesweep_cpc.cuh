@@ -52,7 +52,7 @@ struct CpcShape {
     static constexpr int WORDS = OFF_MISC + 16;
     static constexpr size_t SMEM_BYTES = sizeof(uint32_t) * WORDS + 16;
     static constexpr uint32_t PORTION_MAX = (uint32_t)((((1u << 30) - 1u) / TILE) * TILE);
-    static_assert(TILE <= STAGE_WORDS && H * 16 <= STAGE_WORDS, "reorder buffer and Q alias the staging buffer");
+    static_assert(TILE + TILE / 256 <= STAGE_WORDS && H * 16 <= STAGE_WORDS, "reorder buffer and Q alias the staging buffer");
     static_assert(TILE < 65536, "positions are packed in 16 bits");
 };
 
@@ -214,6 +214,7 @@ onesweep_cpc_kernel(const PassArgs a)
             const uint32_t row = 2u * tid + r;
             const uint4* r4 = reinterpret_cast<const uint4*>(s_mat + row * 32u);
             uint2* q2 = reinterpret_cast<uint2*>(s_stage + row * 16u);
+            uint4* q4 = reinterpret_cast<uint4*>(s_stage + row * 32u);  // 32-bit Q rows (DBG & 16): conflict-free reads
             uint32_t run = start[r] + below[r];
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
@@ -228,7 +229,8 @@ onesweep_cpc_kernel(const PassArgs a)
                 run = __dp4a(v.z, 0x01010101u, run);
                 const uint32_t q3 = run;
                 run = __dp4a(v.w, 0x01010101u, run);
-                q2[grp] = make_uint2(q0 | (q1 << 16), q2v | (q3 << 16));
+                if constexpr ((DBG & 16) != 0) q4[grp] = make_uint4(q0, q1, q2v, q3);
+                else q2[grp] = make_uint2(q0 | (q1 << 16), q2v | (q3 << 16));
             }
         }
     }
@@ -244,7 +246,8 @@ onesweep_cpc_kernel(const PassArgs a)
         for (int j = 0; j < SPC; ++j) {
             const uint32_t off = cell_offset<RB, SHIFT>(key[j], lane4);
             const uint32_t w = *reinterpret_cast<const uint32_t*>(mat_bytes + off);
-            const uint32_t qv = *reinterpret_cast<const uint16_t*>(q_bytes + (off >> 1));
+            const uint32_t qv = (DBG & 16) ? *reinterpret_cast<const uint32_t*>(q_bytes + off)
+                                           : (uint32_t)*reinterpret_cast<const uint16_t*>(q_bytes + (off >> 1));
             const uint32_t r = (rk[j >> 2] >> (8 * (j & 3))) & 0xFFu;
             const uint32_t pos = __dp4a(w & below_mask, 0x01010101u, qv + r);
             if (j & 1) pk[j >> 1] |= pos << 16; else pk[j >> 1] = pos;
@@ -258,6 +261,8 @@ onesweep_cpc_kernel(const PassArgs a)
     for (int j = 0; j < SPC; ++j) {
         uint32_t pos = (j & 1) ? (pk[j >> 1] >> 16) : (pk[j >> 1] & 0xFFFFu);
         if (DBG & 8) pos = (pos & 0x1000u) ? pos : j * THREADS + tid;  // timing experiment: conflict-free scatter
+        if (DBG & 32) pos += pos >> 8;  // skewed reorder layout: one word of padding per 256 positions keeps the columns
+                                        // of a single-bucket (sorted / constant-digit) tile in distinct banks
         s_stage[pos] = key[j];
     }
     LSD_TRACE(6);
@@ -316,7 +321,7 @@ onesweep_cpc_kernel(const PassArgs a)
 #pragma unroll 16
         for (int i = 0; i < TILE / THREADS; ++i) {
             const uint32_t p = i * THREADS + tid;
-            const uint32_t k = s_stage[p];
+            const uint32_t k = s_stage[(DBG & 32) ? p + (p >> 8) : p];
             if (DBG & 2) {  // timing experiment: full-line coalesced stores
                 out[a.portion_base + tile_base + p] = k + s_gbase[(k >> SHIFT) & (H - 1)];
             } else if (DBG & 4) {  // timing experiment: no global stores
@@ -327,7 +332,7 @@ onesweep_cpc_kernel(const PassArgs a)
         }
     } else {
         for (uint32_t p = tid; p < valid; p += THREADS) {
-            const uint32_t k = s_stage[p];
+            const uint32_t k = s_stage[(DBG & 32) ? p + (p >> 8) : p];
             out[s_gbase[(k >> SHIFT) & (H - 1)] + p] = k;
         }
     }

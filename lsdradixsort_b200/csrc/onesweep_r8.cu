@@ -61,6 +61,9 @@ static const OnesweepLauncher kTable[] = {
     make_lpc32_launcher<8, 9, 29, 3, 4, 0, false, true>(),   // 49: single-pass matrix scan (rows kept in registers)
     make_lpc32_launcher<8, 9, 29, 3, 8, 0, false, true>(),   // 50: same, look-back window 8
     make_lpc32_launcher<8, 9, 31, 3, 4, 0, false, true>(),   // 51: single-pass scan, tile 8928
+    make_cpc_launcher<8, 64, 3, 4, 16>(),        // 52: CPC, look-back window 4, 32-bit Q rows
+    make_cpc_launcher<8, 64, 3, 4, 48>(),        // 53: CPC, window 4, 32-bit Q rows, skewed reorder layout
+    make_cpc_launcher<8, 64, 3, 4, 32>(),        // 54: CPC, window 4, skewed reorder layout
 };
 
 const OnesweepLauncher* onesweep_table_r8(int* count)

@@ -127,7 +127,7 @@ class CudaOps:
         self.capacity = capacity
 
     def top_digit_histogram(self, keys: torch.Tensor) -> torch.Tensor:
-        return self.api.digit_histograms(keys, self.r)[-1]  # [256] int64, row of the top digit
+        return self.api.top_digit_histogram(keys, self.r)  # [256] int64
 
     def partition_by_top_digit(self, keys: torch.Tensor, out: torch.Tensor) -> None:
         self.api.sort_pass(keys, out, self.r, 32 // self.r - 1, self.block, workspace=self.sorter.workspace)
@@ -178,12 +178,11 @@ def distributed_sort(keys: torch.Tensor, ops, recv: torch.Tensor, staging: torch
     mark()
     # 1-2. top-digit histograms -> identical bucket map and split sizes on every rank
     local = ops.top_digit_histogram(keys).to(torch.int64)
-    global_hist = local.clone()
-    dist.all_reduce(global_hist, op=dist.ReduceOp.SUM, group=group)  # the MSD-histogram all-reduce
-    gathered = [torch.empty_like(local) for _ in range(nranks)]
-    dist.all_gather(gathered, local, group=group)  # per-rank rows: who sends how much to whom
-    per_rank = torch.stack(gathered).cpu().numpy()
-    owner = assign_buckets(global_hist.cpu().numpy(), nranks)
+    gathered = torch.empty(nranks * BUCKETS, dtype=torch.int64, device=local.device)
+    # one collective: the per-rank rows (who sends how much to whom); their sum is the all-reduced MSD histogram
+    dist.all_gather_into_tensor(gathered, local.contiguous().view(-1), group=group)
+    per_rank = gathered.view(nranks, BUCKETS).cpu().numpy()
+    owner = assign_buckets(per_rank.sum(axis=0), nranks)
     in_splits, out_splits = split_sizes(per_rank, owner, rank)
     n_out = sum(out_splits)
     if n_out > recv.numel():

@@ -86,7 +86,7 @@ def test_sort_skip_disabled_gives_same_result():
 
 
 @pytest.mark.parametrize("kind", ["uniform", "entropy4_table", "all_equal"])
-@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21, 22, 23, 24, 25, 26, 27, 28, 29, 30, 31, 32, 33, 34, 35, 36, 38, 44, 45, 46, 47, 48, 49, 50, 51])
+@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21, 22, 23, 24, 25, 26, 27, 28, 29, 30, 31, 32, 33, 34, 35, 36, 38, 44, 45, 46, 47, 48, 49, 50, 51, 52, 53, 54])
 def test_sort_kernel_variants_r8(variant, kind):
     n = 300_000 + 11
     keys = keygen.make_keys(kind, n, seed=variant)
@@ -404,3 +404,12 @@ def test_sort_pass_scatter_segments_group_buckets_per_tile():
     ga, gb = host(a[:lo_cnt]), host(b[: n - lo_cnt])
     assert np.array_equal(np.sort(ga), np.sort(keys[keys >> 24 < 128]))
     assert np.array_equal(np.sort(gb), np.sort(keys[keys >> 24 >= 128]))
+
+
+@pytest.mark.parametrize("r", [1, 4, 8])
+@pytest.mark.parametrize("n", [0, 5, 100_001])
+def test_top_digit_histogram_is_the_last_row_of_digit_histograms(r, n):
+    keys = keygen.make_keys("uniform", n, seed=3 * r + 1)
+    d = dev(keys) if n else torch.empty(0, dtype=torch.int32, device="cuda")
+    top = L.top_digit_histogram(d, r).cpu().numpy().astype(np.uint64)
+    assert np.array_equal(top, _oracle.digit_histograms(keys, r).reshape(32 // r, 1 << r)[-1])
