@@ -115,7 +115,7 @@ onesweep_lpc_kernel(const PassArgs a)
     constexpr int SCAN_WARPS = S_::ROW_GROUPS < WARPS ? S_::ROW_GROUPS : WARPS;  // warps 0.. own the matrix rows
     constexpr int DT0 = THREADS - ROWS;  // digit-pair threads are the LAST `ROWS` threads of the CTA: they enter the
                                          // rank chain last, so their look-back overlaps the chain of the first warps
-    constexpr int LB = 8;                  // look-back window (predecessor rows fetched per round trip)
+    constexpr int LB = 4;                  // look-back window (predecessor rows fetched per round trip)
     constexpr uint32_t kScanBarrier = 15;  // named barrier: "scan pass 2 done" among the scan warps
 
     if (a.plan->skip[a.pass]) return;

@@ -413,3 +413,29 @@ def test_top_digit_histogram_is_the_last_row_of_digit_histograms(r, n):
     d = dev(keys) if n else torch.empty(0, dtype=torch.int32, device="cuda")
     top = L.top_digit_histogram(d, r).cpu().numpy().astype(np.uint64)
     assert np.array_equal(top, _oracle.digit_histograms(keys, r).reshape(32 // r, 1 << r)[-1])
+
+
+def test_sort_is_cuda_graph_capturable():
+    """The whole sort (memset, histogram, device-side plan, passes, copy-back) is enqueued without host synchronisation,
+    so it can be captured once and replayed: same workspace, new keys each replay."""
+    n = 500_000 + 3
+    s = L.Sorter(n, r=8)
+    buf = torch.empty(n, dtype=torch.int32, device="cuda")
+    first = keygen.make_keys("uniform", n, seed=1)
+    buf.copy_(dev(first))
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        s.sort_(buf)  # warm-up outside capture (function attributes are set on first launch)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        buf.copy_(dev(first))
+        with torch.cuda.graph(g, stream=side):
+            s.sort_(buf)
+    torch.cuda.synchronize()
+    for seed, kind in ((2, "uniform"), (3, "low_nibble"), (4, "sorted")):
+        keys = keygen.make_keys(kind, n, seed=seed)
+        buf.copy_(dev(keys))
+        g.replay()
+        torch.cuda.synchronize()
+        assert np.array_equal(host(buf), _oracle.sort(keys, 8)), kind
