@@ -157,5 +157,9 @@ int main()
         printf("                  sector-misaligned runs %.3f ms | ragged runs, p-linear warps (pass kernels today) %.3f ms | ragged runs, line-aligned warps %.3f ms\n",
                t3, t4, t5);
     }
+    {   // in-place variant of the full-line copy (what an in-place scan does to DRAM: read and write streams share pages)
+        const float t_in = run<0>(in, in, tiles, (size_t)TILE * 4);
+        printf("in-place full-line copy (out == in): %.3f ms (%.0f GB/s)\n", t_in, 8.0 * n / t_in / 1e6);
+    }
     return 0;
 }

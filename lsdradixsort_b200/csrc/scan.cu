@@ -335,7 +335,196 @@ scan_tma_kernel(uint32_t* __restrict__ a, uint64_t n, ScanWorkspace* __restrict_
 #undef SCAN_TRACE
 }
 
-// LSD_SCAN_REGISTER_PATH=1 selects the register-resident kernel (tuning comparisons); unaligned arrays use it too.
+// -------------------------------------------------------------------------------------
+// scan_cluster_kernel: scan_tma_kernel with thread-block clusters of 8 CTAs sharing ONE look-back record.
+//
+// Why (profiles/r01_scan_variants.txt): with ~900 tiles in flight every tile's look-back walks ~18 windows of 32
+// predecessors at ~1 K cycles per round trip -- 18 K of the tile's 31 K-cycle life.  A cluster of 8 CTAs takes 8
+// consecutive tiles; the tile totals are exchanged through distributed shared memory (st.shared::cluster, ~200 cycles),
+// the cluster leader publishes one aggregate and looks back over CLUSTER records (8x fewer in flight: ~4 windows),
+// and hands the cluster's exclusive prefix to its 7 peers through distributed shared memory again.  Three hardware
+// cluster barriers replace ~14 global round trips.
+// -------------------------------------------------------------------------------------
+constexpr int kScanCluster = 8;
+
+__device__ __forceinline__ uint32_t cluster_ctarank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all()
+{
+    __syncwarp();  // the .aligned forms need the warp converged
+    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void st_cluster_u32(const void* local_smem, uint32_t rank, uint32_t v)
+{
+    uint32_t remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(scan_smem_u32(local_smem)), "r"(rank));
+    asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(remote), "r"(v) : "memory");
+}
+
+template <int THREADS>
+__global__ void __cluster_dims__(kScanCluster, 1, 1) __launch_bounds__(THREADS)
+scan_cluster_kernel(uint32_t* __restrict__ a, uint64_t n, ScanWorkspace* __restrict__ ws, uint32_t tiles, uint32_t* __restrict__ trace)
+{
+    const long long t_start = trace ? clock64() : 0;
+#define SCANC_TRACE(slot) do { if (trace && tid == 0 && active) trace[(size_t)tile * 8 + (slot)] = (uint32_t)(clock64() - t_start); } while (0)
+    constexpr int WARPS = THREADS / 32;
+    constexpr int TILE = THREADS * kScanItems;
+    constexpr int P = kScanVecs * WARPS;
+    constexpr int PPL = P / 32;
+    static_assert(P % 32 == 0 && PPL >= 1, "partials must fill warp 0 evenly");
+
+    extern __shared__ __align__(128) uint32_t s_data[];  // [TILE]
+    __shared__ __align__(8) uint64_t s_bar;
+    __shared__ uint32_t s_ticket;                 // cluster ticket, written by the leader into every CTA
+    __shared__ uint32_t s_totals[kScanCluster];   // tile totals of the cluster, written by every CTA into every CTA
+    __shared__ uint32_t s_cluster_prefix;         // exclusive prefix of the cluster, written by the leader into every CTA
+    __shared__ uint32_t s_partial[kScanVecs * WARPS];
+
+    const uint32_t tid = threadIdx.x;
+    const uint32_t lane = tid & 31u;
+    const uint32_t warp = tid >> 5;
+    const uint32_t rank = cluster_ctarank();
+
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(scan_smem_u32(&s_bar)) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    uint32_t my_ticket = 0;
+    if (rank == 0 && tid == 0) my_ticket = atomicAdd(&ws->ticket, 1u);  // in flight across barrier #0
+    cluster_sync_all();  // #0: every CTA of the cluster has started: its shared memory may be written remotely from here on
+    if (rank == 0 && tid < (uint32_t)kScanCluster) {
+        const uint32_t t = __shfl_sync((1u << kScanCluster) - 1u, my_ticket, 0);
+        st_cluster_u32(&s_ticket, tid, t);
+    }
+    cluster_sync_all();  // #1: every CTA knows the cluster's ticket (and its mbarrier is initialised)
+    const uint32_t cluster = s_ticket;
+    const uint32_t tile = cluster * kScanCluster + rank;
+    const bool active = tile < tiles;
+    const uint64_t base = (uint64_t)tile * TILE;
+    const uint64_t left = active ? n - base : 0;
+    const bool full = left >= (uint64_t)TILE;
+    SCANC_TRACE(0);  // ticket known (cluster barrier #1 passed)
+    if (full && tid == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(scan_smem_u32(&s_bar)), "r"(TILE * 4) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(scan_smem_u32(s_data)), "l"(a + base), "r"(TILE * 4), "r"(scan_smem_u32(&s_bar)) : "memory");
+    }
+    if (full) {
+        asm volatile(
+            "{\n.reg .pred p;\nSCANC_WAIT_%=:\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n"
+            "@p bra SCANC_DONE_%=;\nbra SCANC_WAIT_%=;\nSCANC_DONE_%=:\n}\n" ::"r"(scan_smem_u32(&s_bar)) : "memory");
+    } else {
+        for (uint32_t i = tid; i < (uint32_t)TILE; i += THREADS) s_data[i] = i < left ? a[base + i] : 0u;
+        __syncthreads();
+    }
+
+    SCANC_TRACE(1);  // tile landed
+    uint32_t excl[kScanVecs];
+#pragma unroll
+    for (int j = 0; j < kScanVecs; ++j) {
+        const uint4 v = lds128_volatile(s_data + 4 * (j * THREADS + tid));
+        const uint32_t sum = v.x + v.y + v.z + v.w;
+        const uint32_t incl = warp_inclusive_scan(sum, lane);
+        excl[j] = incl - sum;
+        if (lane == 31) s_partial[j * WARPS + warp] = incl;
+    }
+    __syncthreads();
+
+    if (warp == 0) {
+        uint32_t part[PPL];
+        uint32_t lane_sum = 0;
+#pragma unroll
+        for (int k = 0; k < PPL; ++k) {
+            part[k] = s_partial[lane * PPL + k];
+            lane_sum += part[k];
+        }
+        const uint32_t lane_incl = warp_inclusive_scan(lane_sum, lane);
+        const uint32_t tile_total = __shfl_sync(kFullMask, lane_incl, 31);
+        uint32_t run = lane_incl - lane_sum;
+#pragma unroll
+        for (int k = 0; k < PPL; ++k) {
+            s_partial[lane * PPL + k] = run;
+            run += part[k];
+        }
+        if (lane < (uint32_t)kScanCluster) st_cluster_u32(&s_totals[rank], lane, tile_total);  // my total into every CTA
+    }
+    SCANC_TRACE(2);  // partials done, total sent
+    cluster_sync_all();  // #2: all tile totals of the cluster are in every CTA's shared memory
+
+    if (rank == 0 && warp == 0) {
+        uint32_t cluster_total = 0;
+#pragma unroll
+        for (int r = 0; r < kScanCluster; ++r) cluster_total += s_totals[r];
+        uint32_t exclusive = 0;
+        if (cluster == 0) {
+            if (lane == 0) st_relaxed_gpu(&ws->state[0], kFlagInclusive | cluster_total);
+        } else {
+            if (lane == 0) st_relaxed_gpu(&ws->state[cluster], kFlagAggregate | cluster_total);
+            int64_t look = (int64_t)cluster - 1;
+            while (true) {
+                const int64_t idx = look - (int64_t)lane;
+                const uint64_t w = idx >= 0 ? ld_relaxed_gpu(&ws->state[idx]) : kFlagInclusive;  // virtual records: prefix 0
+                const uint32_t ready = __ballot_sync(kFullMask, (w >> 32) != 0);
+                const uint32_t incl_mask = __ballot_sync(kFullMask, (w >> 32) == 2);
+                uint32_t take = (uint32_t)w;
+                bool finished = false;
+                if (incl_mask) {
+                    const uint32_t first = __ffs(incl_mask) - 1;
+                    const uint32_t need = (2u << first) - 1u;
+                    if ((ready & need) != need) continue;
+                    if (lane > first) take = 0;
+                    finished = true;
+                } else if (ready != kFullMask) {
+                    continue;
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) take += __shfl_xor_sync(kFullMask, take, o);
+                exclusive += take;
+                if (finished) break;
+                look -= 32;
+            }
+            if (lane == 0) st_relaxed_gpu(&ws->state[cluster], kFlagInclusive | (uint32_t)(exclusive + cluster_total));
+        }
+        if (lane < (uint32_t)kScanCluster) st_cluster_u32(&s_cluster_prefix, lane, exclusive);
+    }
+    cluster_sync_all();  // #3: the cluster's exclusive prefix is in every CTA; no remote access happens after this point
+
+    SCANC_TRACE(3);  // cluster prefix known (barrier #3 passed)
+    uint32_t tile_prefix = s_cluster_prefix;
+    for (uint32_t r = 0; r < rank; ++r) tile_prefix += s_totals[r];
+    if (!active) return;
+#pragma unroll
+    for (int j = 0; j < kScanVecs; ++j) {
+        const uint4 v = lds128_volatile(s_data + 4 * (j * THREADS + tid));
+        uint32_t run = tile_prefix + s_partial[j * WARPS + warp] + excl[j];
+        uint4 o;
+        o.x = run; run += v.x;
+        o.y = run; run += v.y;
+        o.z = run; run += v.z;
+        o.w = run;
+        const uint64_t e = 4ull * (j * THREADS + tid);
+        if (full) {
+            __stcs(reinterpret_cast<uint4*>(a + base + e), o);
+        } else {
+            if (e + 0 < left) a[base + e + 0] = o.x;
+            if (e + 1 < left) a[base + e + 1] = o.y;
+            if (e + 2 < left) a[base + e + 2] = o.z;
+            if (e + 3 < left) a[base + e + 3] = o.w;
+        }
+    }
+    SCANC_TRACE(4);  // stores issued
+#undef SCANC_TRACE
+}
+
+// LSD_SCAN_CLUSTER=1 selects scan_cluster_kernel (one look-back record per cluster of 8 tiles).  Measured on B200 it does not
+// beat scan_tma_kernel (0.528 vs 0.512 ms at 2^28): the two cluster barriers at the start (all 8 CTAs must have started before
+// their shared memory may be written) and the wait for the slowest of 8 tile loads cost what the shorter look-back saves.
+static const bool g_scan_no_cluster = [] { const char* e = getenv("LSD_SCAN_CLUSTER"); return !(e && e[0] == '1'); }();
 static const bool g_scan_register_path = [] { const char* e = getenv("LSD_SCAN_REGISTER_PATH"); return e && e[0] == '1'; }();
 
 static int scan_threads_for(int block)
@@ -368,6 +557,27 @@ int launch_prefix_sum(uint32_t* a, uint64_t n, int block, void* ws, size_t ws_by
     LSD_CUDA_TRY(cudaMemsetAsync(ws, 0, need, s));
     auto* w = static_cast<ScanWorkspace*>(ws);
     const bool tma = !g_scan_register_path && aligned_to(a, 16);
+    uint32_t* trace_c = g_scan_trace ? reinterpret_cast<uint32_t*>(static_cast<ScanWorkspace*>(ws)->state + tiles) : nullptr;
+    if (tma && !g_scan_no_cluster) {
+        const unsigned grid = (unsigned)((tiles + kScanCluster - 1) / kScanCluster * kScanCluster);
+        const size_t smem_c = (size_t)threads * kScanItems * sizeof(uint32_t);
+        switch (threads) {
+            case 128:
+                LSD_CUDA_TRY(cudaFuncSetAttribute(scan_cluster_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
+                scan_cluster_kernel<128><<<grid, 128, smem_c, s>>>(a, n, w, (uint32_t)tiles, trace_c);
+                break;
+            case 256:
+                LSD_CUDA_TRY(cudaFuncSetAttribute(scan_cluster_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
+                scan_cluster_kernel<256><<<grid, 256, smem_c, s>>>(a, n, w, (uint32_t)tiles, trace_c);
+                break;
+            default:
+                LSD_CUDA_TRY(cudaFuncSetAttribute(scan_cluster_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
+                scan_cluster_kernel<512><<<grid, 512, smem_c, s>>>(a, n, w, (uint32_t)tiles, trace_c);
+                break;
+        }
+        LSD_LAUNCH_CHECK();
+        return LSD_OK;
+    }
     uint32_t* trace = g_scan_trace ? reinterpret_cast<uint32_t*>(w->state + tiles) : nullptr;
     const size_t smem = (size_t)threads * kScanItems * sizeof(uint32_t);
     if (tma) {
