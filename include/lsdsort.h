@@ -121,6 +121,22 @@ LSD_API int lsd_sort(uint32_t *keys, uint32_t *scratch, uint64_t n, int r, int b
 LSD_API int lsd_sort_ex(uint32_t *keys, uint32_t *scratch, uint64_t n, int r, int block, void *ws, size_t ws_bytes,
                         const lsd_sort_options *opt, lsd_stream_t stream);
 
+/* Key-value form of lsd_sort_ex: every key carries a 32-bit value (a row id, an index, any payload) that follows it
+ * through every pass.  keys/vals: n entries in, out; keys_scratch/vals_scratch: n entries of ping-pong space each.
+ * Result: keys ascending, and vals[i] is the value that came with keys[i]; equal keys keep their INPUT order (the
+ * reference states its passes are stable, LSDRadixSort.cu:25-54 -- with keys alone that is unobservable, SURVEY 8(f)2;
+ * with vals = 0..n-1 the output vals are the stable sorting permutation).  The reference's scatter moves keys only
+ * (LSDRadixSort.cu:836); this is the payload extension of the same pass.  Same passes, plan and skipping as lsd_sort;
+ * workspace from lsd_sort_pairs_workspace_bytes (opt may be NULL).  16 B per pair per pass of HBM traffic. */
+LSD_API size_t lsd_sort_pairs_workspace_bytes(uint64_t n, int r, int block, const lsd_sort_options *opt);
+LSD_API int lsd_sort_pairs(uint32_t *keys, uint32_t *vals, uint32_t *keys_scratch, uint32_t *vals_scratch, uint64_t n,
+                           int r, int block, void *ws, size_t ws_bytes, const lsd_sort_options *opt,
+                           lsd_stream_t stream);
+/* lsd_sort_pairs with per-stage device times, as lsd_sort_timed (stage_ms[1+passes] = both copy-backs). */
+LSD_API int lsd_sort_pairs_timed(uint32_t *keys, uint32_t *vals, uint32_t *keys_scratch, uint32_t *vals_scratch,
+                                 uint64_t n, int r, int block, void *ws, size_t ws_bytes, const lsd_sort_options *opt,
+                                 lsd_stream_t stream, float *stage_ms, int stage_cap, int *stages_written);
+
 /* One stable counting-sort pass on digit `bit_group`: out <- in reordered by that digit, keys with
  * equal digits keeping their input order.  Replaces one iteration of the reference's pass loop
  * (LSDRadixSort.cu:845-906; CPU twin LSDRadixSortPass, :25-54, without its copy-back at :53).

@@ -11,6 +11,9 @@ from .api import (  # noqa: F401
     GPULSDRadixSort,
     GPUPrefixSum,
     HostSorter,
+    PairSorter,
+    argsort,
+    sort_pairs_,
     Sorter,
     SortInfo,
     build_histogram,

@@ -81,6 +81,16 @@ def lib() -> C.CDLL:
         "lsd_sort_workspace_bytes_ex": (C.c_size_t, [C.c_uint64, C.c_int, C.c_int, C.POINTER(SortOptions)]),
         "lsd_sort": (C.c_int, [vp, vp, C.c_uint64, C.c_int, C.c_int, vp, C.c_size_t, vp]),
         "lsd_sort_ex": (C.c_int, [vp, vp, C.c_uint64, C.c_int, C.c_int, vp, C.c_size_t, C.POINTER(SortOptions), vp]),
+        "lsd_sort_pairs_workspace_bytes": (C.c_size_t, [C.c_uint64, C.c_int, C.c_int, C.POINTER(SortOptions)]),
+        "lsd_sort_pairs": (
+            C.c_int,
+            [vp, vp, vp, vp, C.c_uint64, C.c_int, C.c_int, vp, C.c_size_t, C.POINTER(SortOptions), vp],
+        ),
+        "lsd_sort_pairs_timed": (
+            C.c_int,
+            [vp, vp, vp, vp, C.c_uint64, C.c_int, C.c_int, vp, C.c_size_t, C.POINTER(SortOptions), vp,
+             C.POINTER(C.c_float), C.c_int, C.POINTER(C.c_int)],
+        ),
         "lsd_sort_pass": (C.c_int, [vp, vp, C.c_uint64, C.c_int, C.c_int, C.c_int, vp, C.c_size_t, vp, vp]),
         "lsd_sort_pass_scatter": (C.c_int, [vp, C.c_uint64, C.c_int, C.c_int, vp, vp, vp, C.c_size_t, vp]),
         "lsd_ipc_export": (C.c_int, [vp, vp, u64p]),

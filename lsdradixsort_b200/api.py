@@ -260,6 +260,64 @@ class Sorter:
         return SortInfo(mask.value, launches.value)
 
 
+class PairSorter:
+    """Key-value sort (lsd_sort_pairs): reusable ping-pong buffers + workspace for up to ``max_n`` pairs."""
+
+    def __init__(self, max_n: int, r: int = 8, block: int = 0, device: Optional[torch.device] = None, **opts):
+        self.max_n, self.r, self.block, self.opts = int(max_n), int(r), int(block), opts
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        o = _options(**opts)
+        nbytes = N.lib().lsd_sort_pairs_workspace_bytes(self.max_n, r, block, C.byref(o) if o else None)
+        if nbytes == 0 and self.max_n > 0:
+            raise N.LsdError(N.LSD_ERR_INVALID_VALUE, "lsd_sort_pairs_workspace_bytes",
+                             "invalid r/block/variant (or a variant without the key-value form) or n too large")
+        self.keys_scratch = torch.empty(max(self.max_n, 1), dtype=torch.int32, device=self.device)
+        self.vals_scratch = torch.empty(max(self.max_n, 1), dtype=torch.int32, device=self.device)
+        self.workspace = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=self.device)
+
+    def _args(self, keys: torch.Tensor, vals: torch.Tensor):
+        _check_keys(keys, "keys")
+        _check_keys(vals, "vals")
+        n = keys.numel()
+        if vals.numel() != n:
+            raise ValueError("keys and vals must have the same length")
+        if n > self.max_n:
+            raise ValueError("more pairs than this PairSorter's capacity")
+        o = _options(**self.opts)
+        return (keys.data_ptr(), vals.data_ptr(), self.keys_scratch.data_ptr(), self.vals_scratch.data_ptr(), n, self.r,
+                self.block, self.workspace.data_ptr(), self.workspace.numel(), C.byref(o) if o else None,
+                _stream_ptr(keys.device))
+
+    def sort_(self, keys: torch.Tensor, vals: torch.Tensor):
+        """Sort ``keys`` ascending in place; ``vals`` is permuted the same way (equal keys keep their input order)."""
+        N.check(N.lib().lsd_sort_pairs(*self._args(keys, vals)), "lsd_sort_pairs")
+        return keys, vals
+
+    def sort_timed_(self, keys: torch.Tensor, vals: torch.Tensor) -> list:
+        stages = 32 // self.r + 2
+        buf = (C.c_float * stages)()
+        written = C.c_int(0)
+        N.check(N.lib().lsd_sort_pairs_timed(*self._args(keys, vals), buf, stages, C.byref(written)),
+                "lsd_sort_pairs_timed")
+        return list(buf)[: written.value]
+
+
+def sort_pairs_(keys: torch.Tensor, vals: torch.Tensor, r: int = 8, block: int = 0, **opts):
+    """In-place key-value sort; allocates scratch for this one call."""
+    _check_keys(keys, "keys")
+    return PairSorter(keys.numel(), r, block, device=keys.device, **opts).sort_(keys, vals)
+
+
+def argsort(keys: torch.Tensor, r: int = 8, block: int = 0, **opts) -> torch.Tensor:
+    """The stable sorting permutation of ``keys`` (int32 indices; ``keys`` is left untouched): values 0..n-1 carried
+    through lsd_sort_pairs.  n < 2^31."""
+    _check_keys(keys, "keys")
+    n = keys.numel()
+    idx = torch.arange(n, dtype=torch.int32, device=keys.device)
+    sort_pairs_(keys.clone(), idx, r, block, **opts)
+    return idx
+
+
 def sort_(keys: torch.Tensor, r: int = 8, block: int = 0, **opts) -> torch.Tensor:
     """Sort ``keys`` in place, ascending as unsigned 32-bit; allocates scratch for this one call."""
     _check_keys(keys, "keys")

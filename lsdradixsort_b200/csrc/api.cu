@@ -150,6 +150,24 @@ LSD_API int lsd_sort(uint32_t* keys, uint32_t* scratch, uint64_t n, int r, int b
     return lsd_sort_ex(keys, scratch, n, r, block, ws, ws_bytes, nullptr, stream);
 }
 
+LSD_API size_t lsd_sort_pairs_workspace_bytes(uint64_t n, int r, int block, const lsd_sort_options* opt)
+{
+    if (opt && opt->struct_bytes != sizeof(lsd_sort_options)) return 0;
+    SortLayout L;
+    if (make_layout(n, r, block, opt, &L, true) != LSD_OK) return 0;
+    return L.total_bytes;
+}
+
+LSD_API int lsd_sort_pairs(uint32_t* keys, uint32_t* vals, uint32_t* keys_scratch, uint32_t* vals_scratch, uint64_t n,
+                           int r, int block, void* ws, size_t ws_bytes, const lsd_sort_options* opt, lsd_stream_t stream)
+{
+    if (opt && opt->struct_bytes != sizeof(lsd_sort_options)) return LSD_ERR_INVALID_VALUE;
+    if (n > 0 && (!vals || !vals_scratch)) return LSD_ERR_INVALID_VALUE;
+    if (n == 0) return valid_radix(r) ? LSD_OK : LSD_ERR_INVALID_VALUE;
+    return sort_enqueue(keys, keys_scratch, n, r, block, ws, ws_bytes, opt, (cudaStream_t)stream, nullptr, nullptr, vals,
+                        vals_scratch);
+}
+
 LSD_API int lsd_sort_pass(const uint32_t* in, uint32_t* out, uint64_t n, int r, int bit_group, int block, void* ws,
                           size_t ws_bytes, uint64_t* hist_out, lsd_stream_t stream)
 {
@@ -204,9 +222,9 @@ LSD_API int lsd_ipc_close(void* peer_ptr, uint64_t offset)
     return LSD_OK;
 }
 
-LSD_API int lsd_sort_timed(uint32_t* keys, uint32_t* scratch, uint64_t n, int r, int block, void* ws, size_t ws_bytes,
-                           const lsd_sort_options* opt, lsd_stream_t stream, float* stage_ms, int stage_cap,
-                           int* stages_written)
+static int sort_timed_impl(uint32_t* keys, uint32_t* vals, uint32_t* scratch, uint32_t* vals_scratch, uint64_t n, int r,
+                           int block, void* ws, size_t ws_bytes, const lsd_sort_options* opt, lsd_stream_t stream,
+                           float* stage_ms, int stage_cap, int* stages_written)
 {
     if (opt && opt->struct_bytes != sizeof(lsd_sort_options)) return LSD_ERR_INVALID_VALUE;
     if (!valid_radix(r) || !stage_ms) return LSD_ERR_INVALID_VALUE;
@@ -219,7 +237,8 @@ LSD_API int lsd_sort_timed(uint32_t* keys, uint32_t* scratch, uint64_t n, int r,
     if (n == 0) {
         for (int i = 0; i < stages; ++i) stage_ms[i] = 0.f;
     } else {
-        rc = sort_enqueue(keys, scratch, n, r, block, ws, ws_bytes, opt, (cudaStream_t)stream, ev, nullptr);
+        rc = sort_enqueue(keys, scratch, n, r, block, ws, ws_bytes, opt, (cudaStream_t)stream, ev, nullptr, vals,
+                          vals_scratch);
         if (rc == LSD_OK) {
             cudaError_t e = cudaEventSynchronize(ev[stages]);
             if (e != cudaSuccess) { set_last_cuda_error(e); rc = LSD_ERR_CUDA; }
@@ -233,6 +252,23 @@ LSD_API int lsd_sort_timed(uint32_t* keys, uint32_t* scratch, uint64_t n, int r,
     for (int i = 0; i < stages + 1; ++i) cudaEventDestroy(ev[i]);
     if (stages_written) *stages_written = stages;
     return rc;
+}
+
+LSD_API int lsd_sort_timed(uint32_t* keys, uint32_t* scratch, uint64_t n, int r, int block, void* ws, size_t ws_bytes,
+                           const lsd_sort_options* opt, lsd_stream_t stream, float* stage_ms, int stage_cap,
+                           int* stages_written)
+{
+    return sort_timed_impl(keys, nullptr, scratch, nullptr, n, r, block, ws, ws_bytes, opt, stream, stage_ms, stage_cap,
+                           stages_written);
+}
+
+LSD_API int lsd_sort_pairs_timed(uint32_t* keys, uint32_t* vals, uint32_t* keys_scratch, uint32_t* vals_scratch,
+                                 uint64_t n, int r, int block, void* ws, size_t ws_bytes, const lsd_sort_options* opt,
+                                 lsd_stream_t stream, float* stage_ms, int stage_cap, int* stages_written)
+{
+    if (n > 0 && (!vals || !vals_scratch)) return LSD_ERR_INVALID_VALUE;
+    return sort_timed_impl(keys, vals, keys_scratch, vals_scratch, n, r, block, ws, ws_bytes, opt, stream, stage_ms,
+                           stage_cap, stages_written);
 }
 
 LSD_API int lsd_sort_read_plan(const void* ws, uint64_t n, int r, uint32_t* skipped_mask, int* launches,

@@ -61,7 +61,11 @@ struct PassArgs {
     unsigned long long* trace;  // optional per-tile phase clocks (tuning aid), else nullptr
     const uint64_t* dst_ptrs;   // peer-scatter mode only: [H] device pointers, one per bucket (equal inside a segment)
     const uint32_t* dst_seg;    // peer-scatter mode only: [H] first | last << 16 bucket of the bucket's segment, or nullptr
+    uint32_t* vals;             // pairs mode only: the caller's value buffer (travels with `keys`)
+    uint32_t* vals_scratch;     // pairs mode only: ping-pong buffer of the values (travels with `scratch`)
 };
+
+constexpr int kPassPlain = 0, kPassPeer = 1, kPassPairs = 2;
 
 enum MatchMode { kMatchBallot = 0, kMatchHw = 1 };
 
@@ -94,7 +98,7 @@ struct OnesweepShape {
     static constexpr uint32_t PORTION_MAX = (uint32_t)((((1u << 30) - 1u) / TILE) * TILE);
 };
 
-template <int RB, int THREADS, int ITEMS, int MODE>
+template <int RB, int THREADS, int ITEMS, int MODE, bool PAIRS = false>
 __global__ void __launch_bounds__(THREADS)
 onesweep_kernel(const PassArgs a)
 {
@@ -249,7 +253,44 @@ onesweep_kernel(const PassArgs a)
     __syncthreads();
 
     // ---- 6. stream the reorder buffer out, coalesced per bucket ----
-    if (valid == (uint32_t)TILE) {
+    if constexpr (PAIRS) {
+        // keys out, remembering the digit of every position this thread copies: the value of the key at tile
+        // position p goes to the same global index.  Then the values take the keys' route through the reorder
+        // buffer (same warp-striped ownership, same bucket offset + rank), so every pass moves (key, value) together.
+        static_assert(!PAIRS || RB <= 8, "digits are packed four to a register");
+        uint32_t dpk[(ITEMS + 3) / 4];
+#pragma unroll
+        for (int i = 0; i < ITEMS; ++i) {
+            const uint32_t p = i * THREADS + tid;
+            uint32_t d = 0;
+            if (p < valid) {
+                const uint32_t k = s_keys[p];
+                d = digit_of<RB>(k, a.shift);
+                out[s_gbase[d] + p] = k;
+            }
+            if (i & 3) dpk[i >> 2] |= d << (8 * (i & 3)); else dpk[i >> 2] = d;
+        }
+        __syncthreads();  // every key has left the reorder buffer
+        const uint32_t* __restrict__ vin = (src_scratch ? a.vals_scratch : a.vals) + a.portion_base;
+        uint32_t* __restrict__ vout = src_scratch ? a.vals : a.vals_scratch;
+        {
+            const uint32_t off = warp * (32u * ITEMS) + lane;
+            const uint32_t* src = vin + tile_base + off;
+            const uint32_t* wh = s_whist + warp * H;
+#pragma unroll
+            for (int i = 0; i < ITEMS; ++i) {
+                const uint32_t v = (off + i * 32u < valid) ? ld_stream_u32(src + i * 32) : 0u;
+                s_keys[wh[digit_of<RB>(key[i], a.shift)] + rank[i]] = v;
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < ITEMS; ++i) {
+            const uint32_t p = i * THREADS + tid;
+            const uint32_t d = (dpk[i >> 2] >> (8 * (i & 3))) & 0xFFu;
+            if (p < valid) vout[s_gbase[d] + p] = s_keys[p];
+        }
+    } else if (valid == (uint32_t)TILE) {
 #pragma unroll
         for (int i = 0; i < ITEMS; ++i) {
             const uint32_t p = i * THREADS + tid;
@@ -279,25 +320,32 @@ struct OnesweepLauncher {
     size_t smem_bytes;
     int (*launch)(const PassArgs& a, cudaStream_t s);
     int (*launch_peer)(const PassArgs& a, cudaStream_t s);  // bucket-pointer scatter (multi-GPU exchange), or nullptr
+    int (*launch_pairs)(const PassArgs& a, cudaStream_t s);  // key-value pass, or nullptr
 };
 
-template <int RB, int THREADS, int ITEMS, int MODE>
+template <int RB, int THREADS, int ITEMS, int MODE, bool PAIRS = false>
 int onesweep_launch(const PassArgs& a, cudaStream_t s)
 {
     using S = OnesweepShape<RB, THREADS, ITEMS>;
-    LSD_CUDA_TRY(cudaFuncSetAttribute(onesweep_kernel<RB, THREADS, ITEMS, MODE>,
+    LSD_CUDA_TRY(cudaFuncSetAttribute(onesweep_kernel<RB, THREADS, ITEMS, MODE, PAIRS>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::SMEM_BYTES));
-    onesweep_kernel<RB, THREADS, ITEMS, MODE><<<a.tiles, THREADS, S::SMEM_BYTES, s>>>(a);
+    onesweep_kernel<RB, THREADS, ITEMS, MODE, PAIRS><<<a.tiles, THREADS, S::SMEM_BYTES, s>>>(a);
     LSD_LAUNCH_CHECK();
     return LSD_OK;
 }
 
-template <int RB, int THREADS, int ITEMS, int MODE>
+// WITH_PAIRS: also instantiate the key-value form of the kernel (the default shape of every radix has it).
+template <int RB, int THREADS, int ITEMS, int MODE, bool WITH_PAIRS = false>
 constexpr OnesweepLauncher make_launcher()
 {
     using S = OnesweepShape<RB, THREADS, ITEMS>;
-    return OnesweepLauncher{RB, THREADS, ITEMS, MODE, (uint32_t)S::TILE, S::PORTION_MAX, S::SMEM_BYTES,
-                            &onesweep_launch<RB, THREADS, ITEMS, MODE>};
+    if constexpr (WITH_PAIRS)
+        return OnesweepLauncher{RB, THREADS, ITEMS, MODE, (uint32_t)S::TILE, S::PORTION_MAX, S::SMEM_BYTES,
+                                &onesweep_launch<RB, THREADS, ITEMS, MODE>, nullptr,
+                                &onesweep_launch<RB, THREADS, ITEMS, MODE, true>};
+    else
+        return OnesweepLauncher{RB, THREADS, ITEMS, MODE, (uint32_t)S::TILE, S::PORTION_MAX, S::SMEM_BYTES,
+                                &onesweep_launch<RB, THREADS, ITEMS, MODE>, nullptr, nullptr};
 }
 
 // Tables defined in onesweep_r{1,2,4,8}.cu.  Entry 0 of each table is the default shape.

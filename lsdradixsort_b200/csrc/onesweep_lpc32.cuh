@@ -60,10 +60,12 @@ __device__ __forceinline__ uint32_t cell_offset(uint32_t key, uint32_t lane4)
     return (x & mask) | lane4;
 }
 
-template <int RB, int WARPS, int ITEMS, int MINB, int SHIFT, int LB, int CLR, bool PEER, bool SP>
+template <int RB, int WARPS, int ITEMS, int MINB, int SHIFT, int LB, int CLR, int MODE, bool SP>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
 onesweep_lpc32_kernel(const PassArgs a)
 {
+    constexpr bool PEER = MODE == kPassPeer;    // bucket-pointer scatter (multi-GPU exchange)
+    constexpr bool PAIRS = MODE == kPassPairs;  // a 32-bit value travels with every key
     using S_ = Lpc32Shape<RB, WARPS, ITEMS>;
     constexpr int H = S_::H, THREADS = S_::THREADS, S = S_::S, TILE = S_::TILE;
     constexpr int SW = S_::SW, GPW = S_::GPW, LBT = S_::LBT, LBW = S_::LBW;
@@ -422,6 +424,58 @@ onesweep_lpc32_kernel(const PassArgs a)
             for (uint32_t p = lo - mis + tid; (int32_t)(p - hi) < 0; p += THREADS)
                 if ((int32_t)(p - lo) >= 0) dst[gb + p] = s_keys[p];
         }
+    } else if constexpr (PAIRS) {
+        // keys out, remembering the digit of every position this thread copies (the values go to the same place)
+        uint32_t dpk[(ITEMS + 3) / 4];
+#pragma unroll
+        for (int i = 0; i < ITEMS; ++i) {
+            const uint32_t p = i * THREADS + tid;
+            uint32_t d = 0;
+            if (p < valid) {
+                const uint32_t k = s_keys[p];
+                d = (k >> SHIFT) & (H - 1);
+                out[s_gbase[d] + p] = k;
+            }
+            if (i & 3) dpk[i >> 2] |= d << (8 * (i & 3)); else dpk[i >> 2] = d;
+        }
+        // every thread orders its generic accesses to the reorder buffer before the async-proxy write that follows
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();  // every key has left the reorder buffer: it becomes the staging buffer of the values
+        const uint32_t* __restrict__ vin = (src_scratch ? a.vals_scratch : a.vals) + a.portion_base;
+        uint32_t* __restrict__ vout = src_scratch ? a.vals : a.vals_scratch;
+        if (valid == (uint32_t)TILE) {
+            if (tid == 0) {
+                mbar_expect_tx(s_bar, TILE * 4);
+                tma_bulk_g2s(s_keys, vin + tile_base, TILE * 4, s_bar);
+            }
+            mbar_wait(s_bar, 1);
+        } else {
+            for (uint32_t p = tid; p < (uint32_t)TILE; p += THREADS) s_keys[p] = p < valid ? vin[tile_base + p] : 0u;
+            __syncthreads();
+        }
+        // same lane-blocked ownership as the keys, same byte offsets (rk) in the reorder buffer
+        uint32_t val[ITEMS];
+        {
+            const uint32_t* src = s_keys + lane * S + warp * ITEMS;
+#pragma unroll
+            for (int i = 0; i < ITEMS; ++i) val[i] = src[i];
+        }
+        __syncthreads();
+        {
+            char* kb = reinterpret_cast<char*>(s_keys);
+#pragma unroll
+            for (int i = 0; i < ITEMS; ++i) {
+                const uint32_t off = (i & 1) ? (rk[i >> 1] >> 16) : (rk[i >> 1] & 0xFFFFu);
+                *reinterpret_cast<uint32_t*>(kb + off) = val[i];
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < ITEMS; ++i) {
+            const uint32_t p = i * THREADS + tid;
+            const uint32_t d = (dpk[i >> 2] >> (8 * (i & 3))) & 0xFFu;
+            if (p < valid) vout[s_gbase[d] + p] = s_keys[p];
+        }
     } else if (valid == (uint32_t)TILE) {
 #pragma unroll
         for (int i = 0; i < ITEMS; ++i) {
@@ -439,11 +493,11 @@ onesweep_lpc32_kernel(const PassArgs a)
 #undef LSD_TRACE
 }
 
-template <int RB, int WARPS, int ITEMS, int MINB, int SHIFT, int LB, int CLR, bool PEER, bool SP>
+template <int RB, int WARPS, int ITEMS, int MINB, int SHIFT, int LB, int CLR, int MODE, bool SP>
 int onesweep_lpc32_launch_shift(const PassArgs& a, cudaStream_t s)
 {
     using S_ = Lpc32Shape<RB, WARPS, ITEMS>;
-    auto kern = onesweep_lpc32_kernel<RB, WARPS, ITEMS, MINB, SHIFT, LB, CLR, PEER, SP>;
+    auto kern = onesweep_lpc32_kernel<RB, WARPS, ITEMS, MINB, SHIFT, LB, CLR, MODE, SP>;
     LSD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S_::SMEM_BYTES));
     LSD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     kern<<<a.tiles, S_::THREADS, S_::SMEM_BYTES, s>>>(a);
@@ -451,15 +505,15 @@ int onesweep_lpc32_launch_shift(const PassArgs& a, cudaStream_t s)
     return LSD_OK;
 }
 
-template <int RB, int WARPS, int ITEMS, int MINB, int LB, int CLR, bool PEER, bool SP>
+template <int RB, int WARPS, int ITEMS, int MINB, int LB, int CLR, int MODE, bool SP>
 int onesweep_lpc32_launch(const PassArgs& a, cudaStream_t s)
 {
     static_assert(RB == 8, "shift dispatch below is written for 8-bit digits");
     switch (a.shift) {
-        case 0: return onesweep_lpc32_launch_shift<RB, WARPS, ITEMS, MINB, 0, LB, CLR, PEER, SP>(a, s);
-        case 8: return onesweep_lpc32_launch_shift<RB, WARPS, ITEMS, MINB, 8, LB, CLR, PEER, SP>(a, s);
-        case 16: return onesweep_lpc32_launch_shift<RB, WARPS, ITEMS, MINB, 16, LB, CLR, PEER, SP>(a, s);
-        case 24: return onesweep_lpc32_launch_shift<RB, WARPS, ITEMS, MINB, 24, LB, CLR, PEER, SP>(a, s);
+        case 0: return onesweep_lpc32_launch_shift<RB, WARPS, ITEMS, MINB, 0, LB, CLR, MODE, SP>(a, s);
+        case 8: return onesweep_lpc32_launch_shift<RB, WARPS, ITEMS, MINB, 8, LB, CLR, MODE, SP>(a, s);
+        case 16: return onesweep_lpc32_launch_shift<RB, WARPS, ITEMS, MINB, 16, LB, CLR, MODE, SP>(a, s);
+        case 24: return onesweep_lpc32_launch_shift<RB, WARPS, ITEMS, MINB, 24, LB, CLR, MODE, SP>(a, s);
     }
     return LSD_ERR_INVALID_VALUE;
 }
@@ -472,11 +526,12 @@ constexpr OnesweepLauncher make_lpc32_launcher()
     using S_ = Lpc32Shape<RB, WARPS, ITEMS>;
     if constexpr (WITH_PEER)
         return OnesweepLauncher{RB, S_::THREADS, ITEMS, kModeLpc32, (uint32_t)S_::TILE, S_::PORTION_MAX, S_::SMEM_BYTES,
-                                &onesweep_lpc32_launch<RB, WARPS, ITEMS, MINB, LB, CLR, false, SP>,
-                                &onesweep_lpc32_launch<RB, WARPS, ITEMS, MINB, LB, CLR, true, SP>};
+                                &onesweep_lpc32_launch<RB, WARPS, ITEMS, MINB, LB, CLR, kPassPlain, SP>,
+                                &onesweep_lpc32_launch<RB, WARPS, ITEMS, MINB, LB, CLR, kPassPeer, SP>,
+                                &onesweep_lpc32_launch<RB, WARPS, ITEMS, MINB, LB, CLR, kPassPairs, SP>};
     else
         return OnesweepLauncher{RB, S_::THREADS, ITEMS, kModeLpc32, (uint32_t)S_::TILE, S_::PORTION_MAX, S_::SMEM_BYTES,
-                                &onesweep_lpc32_launch<RB, WARPS, ITEMS, MINB, LB, CLR, false, SP>, nullptr};
+                                &onesweep_lpc32_launch<RB, WARPS, ITEMS, MINB, LB, CLR, kPassPlain, SP>, nullptr, nullptr};
 }
 
 }  // namespace lsd

@@ -4,10 +4,10 @@
 namespace lsd {
 
 static const OnesweepLauncher kTable[] = {
-    make_launcher<1, 256, 16, kMatchBallot>(),
-    make_launcher<1, 128, 16, kMatchBallot>(),
-    make_launcher<1, 512, 16, kMatchBallot>(),
-    make_launcher<1, 1024, 8, kMatchBallot>(),
+    make_launcher<1, 256, 16, kMatchBallot, true>(),
+    make_launcher<1, 128, 16, kMatchBallot, true>(),
+    make_launcher<1, 512, 16, kMatchBallot, true>(),
+    make_launcher<1, 1024, 8, kMatchBallot, true>(),
 };
 
 const OnesweepLauncher* onesweep_table_r1(int* count)

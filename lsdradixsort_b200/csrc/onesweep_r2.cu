@@ -4,10 +4,10 @@
 namespace lsd {
 
 static const OnesweepLauncher kTable[] = {
-    make_launcher<2, 256, 16, kMatchBallot>(),
-    make_launcher<2, 128, 16, kMatchBallot>(),
-    make_launcher<2, 512, 16, kMatchBallot>(),
-    make_launcher<2, 1024, 8, kMatchBallot>(),
+    make_launcher<2, 256, 16, kMatchBallot, true>(),
+    make_launcher<2, 128, 16, kMatchBallot, true>(),
+    make_launcher<2, 512, 16, kMatchBallot, true>(),
+    make_launcher<2, 1024, 8, kMatchBallot, true>(),
 };
 
 const OnesweepLauncher* onesweep_table_r2(int* count)

@@ -4,10 +4,10 @@
 namespace lsd {
 
 static const OnesweepLauncher kTable[] = {
-    make_launcher<4, 256, 16, kMatchBallot>(),
-    make_launcher<4, 128, 16, kMatchBallot>(),
-    make_launcher<4, 512, 16, kMatchBallot>(),
-    make_launcher<4, 1024, 8, kMatchBallot>(),
+    make_launcher<4, 256, 16, kMatchBallot, true>(),
+    make_launcher<4, 128, 16, kMatchBallot, true>(),
+    make_launcher<4, 512, 16, kMatchBallot, true>(),
+    make_launcher<4, 1024, 8, kMatchBallot, true>(),
 };
 
 const OnesweepLauncher* onesweep_table_r4(int* count)

@@ -11,7 +11,7 @@ namespace lsd {
 static const OnesweepLauncher kTable[] = {
     make_lpc32_launcher<8, 9, 29, 3, 4, 0, true>(),  // 0: default -- LPC ranking, 32-bit byte-offset counters, look-back window 4 (= variant 30)
     make_launcher<8, 128, 24, kMatchBallot>(),   // 1
-    make_launcher<8, 256, 24, kMatchBallot>(),   // 2
+    make_launcher<8, 256, 24, kMatchBallot, true>(),   // 2
     make_launcher<8, 1024, 8, kMatchBallot>(),   // 3
     make_launcher<8, 256, 16, kMatchBallot>(),   // 4
     make_launcher<8, 512, 16, kMatchHw>(),       // 5: match.any instead of 8 ballots
@@ -37,7 +37,7 @@ static const OnesweepLauncher kTable[] = {
     make_lpc32_launcher<8, 9, 21, 3>(),          // 25: tile 6048
     make_lpc_launcher<8, 9, 21, 4>(),            // 26: packed, tile 6048, 4 CTAs/SM
     make_lpc_launcher<8, 9, 23, 4>(),            // 27: packed, tile 6624, 4 CTAs/SM
-    make_launcher<8, 512, 16, kMatchBallot>(),   // 28: warp-multisplit (ballot) kernel, the round-1 v1 default
+    make_launcher<8, 512, 16, kMatchBallot, true>(),   // 28: warp-multisplit (ballot) kernel, the round-1 v1 default
     make_lpc32_launcher<8, 9, 29, 3, 16>(),      // 29: look-back window 16
     make_lpc32_launcher<8, 9, 29, 3, 4>(),       // 30: look-back window 4
     make_lpc32_launcher<8, 9, 29, 3, 2>(),       // 31: look-back window 2

@@ -89,17 +89,18 @@ static const OnesweepLauncher* table_for(int r, int* count)
     return nullptr;
 }
 
-const OnesweepLauncher* select_launcher(int r, int block, uint32_t variant)
+const OnesweepLauncher* select_launcher(int r, int block, uint32_t variant, bool pairs)
 {
     int count = 0;
     const OnesweepLauncher* t = table_for(r, &count);
     if (!t) return nullptr;
-    if (variant != 0) return variant < (uint32_t)count ? &t[variant] : nullptr;
-    if (block <= 0) return &t[0];
+    if (variant != 0) return (variant < (uint32_t)count && (!pairs || t[variant].launch_pairs)) ? &t[variant] : nullptr;
+    if (block <= 0) return &t[0];  // entry 0 of every table has the key-value form
     // `block` is the reference's threads-per-block knob: pick the warp-multisplit shape with exactly that many
     // threads if there is one, else the shape (of any family) whose CTA size is closest.
     const OnesweepLauncher* best = nullptr;
     for (int i = 0; i < count; ++i) {
+        if (pairs && !t[i].launch_pairs) continue;
         if (t[i].mode == kMatchBallot && t[i].threads == block) return &t[i];
         if (!best || std::abs(t[i].threads - block) < std::abs(best->threads - block)) best = &t[i];
     }
@@ -108,13 +109,13 @@ const OnesweepLauncher* select_launcher(int r, int block, uint32_t variant)
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-int make_layout(uint64_t n, int r, int block, const lsd_sort_options* opt, SortLayout* L)
+int make_layout(uint64_t n, int r, int block, const lsd_sort_options* opt, SortLayout* L, bool pairs)
 {
     if (!valid_radix(r)) return LSD_ERR_INVALID_VALUE;
     if (block < 0 || block > 1024) return LSD_ERR_INVALID_VALUE;
     if (n >= (1ull << 32)) return LSD_ERR_UNSUPPORTED;  // 32-bit scatter indices in this build
     const uint32_t variant = opt ? opt->variant : 0u;
-    const OnesweepLauncher* k = select_launcher(r, block, variant);
+    const OnesweepLauncher* k = select_launcher(r, block, variant, pairs);
     if (!k) return LSD_ERR_INVALID_VALUE;
     L->k = k;
     L->passes = 32 / r;
@@ -146,16 +147,20 @@ int make_layout(uint64_t n, int r, int block, const lsd_sort_options* opt, SortL
 // the sort
 // -------------------------------------------------------------------------------------
 int sort_enqueue(uint32_t* keys, uint32_t* scratch, uint64_t n, int r, int block, void* ws, size_t ws_bytes,
-                 const lsd_sort_options* opt, cudaStream_t s, cudaEvent_t* events, int* launches)
+                 const lsd_sort_options* opt, cudaStream_t s, cudaEvent_t* events, int* launches, uint32_t* vals,
+                 uint32_t* vals_scratch)
 {
+    const bool pairs = vals != nullptr || vals_scratch != nullptr;
     SortLayout L;
-    const int st = make_layout(n, r, block, opt, &L);
+    const int st = make_layout(n, r, block, opt, &L, pairs);
     if (st != LSD_OK) return st;
     if (launches) *launches = 0;
     if (n == 0) return LSD_OK;
     if (!keys || !scratch || !ws) return LSD_ERR_INVALID_VALUE;
+    if (pairs && (!vals || !vals_scratch)) return LSD_ERR_INVALID_VALUE;
     if (ws_bytes < L.total_bytes) return LSD_ERR_WORKSPACE_TOO_SMALL;
     if (!aligned_to(keys, 16) || !aligned_to(scratch, 16) || !aligned_to(ws, 256)) return LSD_ERR_ALIGNMENT;
+    if (pairs && (!aligned_to(vals, 16) || !aligned_to(vals_scratch, 16))) return LSD_ERR_ALIGNMENT;
 
     char* w = static_cast<char*>(ws);
     SortPlan* plan = reinterpret_cast<SortPlan*>(w + L.off_plan);
@@ -197,7 +202,9 @@ int sort_enqueue(uint32_t* keys, uint32_t* scratch, uint64_t n, int r, int block
                           ? reinterpret_cast<unsigned long long*>(opt->debug_trace) : nullptr;
             a.dst_ptrs = nullptr;
             a.dst_seg = nullptr;
-            rc = L.k->launch(a, s);
+            a.vals = vals;
+            a.vals_scratch = vals_scratch;
+            rc = pairs ? L.k->launch_pairs(a, s) : L.k->launch(a, s);
             if (rc != LSD_OK) return rc;
             ++nl;
             lb += (size_t)a.tiles * L.H;
@@ -209,6 +216,11 @@ int sort_enqueue(uint32_t* keys, uint32_t* scratch, uint64_t n, int r, int block
     copy_back_kernel<<<copy_grid, 256, 0, s>>>(keys, scratch, n, plan);
     LSD_LAUNCH_CHECK();
     ++nl;
+    if (pairs) {
+        copy_back_kernel<<<copy_grid, 256, 0, s>>>(vals, vals_scratch, n, plan);
+        LSD_LAUNCH_CHECK();
+        ++nl;
+    }
     if (events) LSD_CUDA_TRY(cudaEventRecord(events[ev++], s));
     if (launches) *launches = nl;
     return LSD_OK;
@@ -300,6 +312,8 @@ int pass_enqueue(const uint32_t* in, uint32_t* out, uint64_t n, int r, int bit_g
         a.trace = nullptr;
         a.dst_ptrs = dst_ptrs;
         a.dst_seg = dst_seg;
+        a.vals = nullptr;
+        a.vals_scratch = nullptr;
         rc = peer ? L.k->launch_peer(a, s) : L.k->launch(a, s);
         if (rc != LSD_OK) return rc;
         lb += (size_t)a.tiles * L.H;

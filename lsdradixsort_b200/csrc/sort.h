@@ -16,12 +16,13 @@ struct SortLayout {
     size_t off_plan, off_hist, off_bases, off_tickets, off_lookback, total_bytes;
 };
 
-int make_layout(uint64_t n, int r, int block, const lsd_sort_options* opt, SortLayout* L);
+int make_layout(uint64_t n, int r, int block, const lsd_sort_options* opt, SortLayout* L, bool pairs = false);
 
-// Enqueue the whole sort on `s`.  If `events` is non-null it must hold passes + 3 events; they are
+// Enqueue the whole sort on `s`.  With vals / vals_scratch non-null every key carries a 32-bit value (key-value sort).  If `events` is non-null it must hold passes + 3 events; they are
 // recorded before the histogram, after the plan, after every pass and after the copy-back.
 int sort_enqueue(uint32_t* keys, uint32_t* scratch, uint64_t n, int r, int block, void* ws, size_t ws_bytes,
-                 const lsd_sort_options* opt, cudaStream_t s, cudaEvent_t* events, int* launches);
+                 const lsd_sort_options* opt, cudaStream_t s, cudaEvent_t* events, int* launches,
+                 uint32_t* vals = nullptr, uint32_t* vals_scratch = nullptr);
 
 // One stable pass on `bit_group` from `in` to `out` (no plan, never skipped).  With dst_ptrs != nullptr the pass
 // runs in peer-scatter mode instead (see lsd_sort_pass_scatter in include/lsdsort.h); `out` and `hist_out` are unused.

@@ -87,6 +87,49 @@ ORACLE_API int lsd_oracle_sort(uint32_t *in, uint32_t *out, int64_t count,
 }
 
 /*
+ * Key-value form of LSDRadixSortPass / LSDRadixSort (LSDRadixSort.cu:25-54, :62-69).
+ * The reference moves keys only (`out[--histogram[digit]] = in[i]`, :45-50); its passes are stable by
+ * construction (backwards walk over inclusive bucket ends).  Carrying a 32-bit value through the SAME
+ * slot assignment makes that stability observable: this is the reference's pass with one more array
+ * written at the identical index, nothing else changed.  Checker for lsd_sort_pairs; the keys it
+ * produces are checked against lsd_oracle_sort / the compiled reference, the values against a stable
+ * argsort (tests/test_oracle.py).
+ */
+ORACLE_API void lsd_oracle_sort_pairs_pass(uint32_t *in, uint32_t *vin, uint32_t *out, uint32_t *vout,
+                                           int64_t count, uint32_t *histogram, int r, int bit_group)
+{
+    const size_t buckets = (size_t)1 << r;
+    memset(histogram, 0, buckets * sizeof(uint32_t));
+    for (int64_t i = 0; i < count; ++i)
+        histogram[oracle_digit(in[i], r, bit_group)] += 1u;
+    uint32_t running = 0;
+    for (size_t b = 0; b < buckets; ++b) {
+        running += histogram[b];
+        histogram[b] = running;
+    }
+    for (int64_t i = count; i-- > 0;) {
+        const uint32_t key = in[i];
+        const uint32_t slot = --histogram[oracle_digit(key, r, bit_group)];
+        out[slot] = key;
+        vout[slot] = vin[i];
+    }
+    if (count > 0) {
+        memcpy(in, out, (size_t)count * sizeof(uint32_t));
+        memcpy(vin, vout, (size_t)count * sizeof(uint32_t));
+    }
+}
+
+ORACLE_API int lsd_oracle_sort_pairs(uint32_t *in, uint32_t *vin, uint32_t *out, uint32_t *vout,
+                                     int64_t count, uint32_t *histogram, int r)
+{
+    if (r <= 0 || r >= 32 || (32 % r) != 0)
+        return -1;
+    for (int g = 0; g < 32 / r; ++g)
+        lsd_oracle_sort_pairs_pass(in, vin, out, vout, count, histogram, r, g);
+    return 0;
+}
+
+/*
  * LSDRadixSort.cu:128-139 PrefixSum.
  * In-place EXCLUSIVE scan with uint32 wrap-around: a[i] <- sum of the original
  * a[0..i) mod 2^32, a[0] <- 0.  (The reference does an inclusive sweep then a

@@ -39,6 +39,8 @@ def oracle() -> C.CDLL:
         l.lsd_oracle_sort_pass.argtypes = [_u32p, _u32p, C.c_int64, _u32p, C.c_int, C.c_int]
         l.lsd_oracle_sort.restype = C.c_int
         l.lsd_oracle_sort.argtypes = [_u32p, _u32p, C.c_int64, _u32p, C.c_int]
+        l.lsd_oracle_sort_pairs.restype = C.c_int
+        l.lsd_oracle_sort_pairs.argtypes = [_u32p, _u32p, _u32p, _u32p, C.c_int64, _u32p, C.c_int]
         l.lsd_oracle_prefix_sum.restype = None
         l.lsd_oracle_prefix_sum.argtypes = [_u32p, C.c_int64]
         l.lsd_oracle_build_histograms.restype = None
@@ -89,6 +91,17 @@ def sort(keys: np.ndarray, r: int = 8) -> np.ndarray:
     assert rc == 0, "oracle rejected r"
     assert np.array_equal(a, out), "reference post-condition: in and out both hold the result"
     return out
+
+
+def sort_pairs(keys: np.ndarray, vals: np.ndarray, r: int = 8):
+    """(sorted keys, values carried along): the reference's pass with a payload written at the same slot."""
+    a = np.ascontiguousarray(keys, dtype=np.uint32).copy()
+    v = np.ascontiguousarray(vals, dtype=np.uint32).copy()
+    out, vout = np.empty_like(a), np.empty_like(v)
+    hist = np.zeros(1 << r, dtype=np.uint32)
+    rc = oracle().lsd_oracle_sort_pairs(a, v, out, vout, a.size, hist, r)
+    assert rc == 0, "oracle rejected r"
+    return out, vout
 
 
 def prefix_sum(a: np.ndarray) -> np.ndarray:
