@@ -1,6 +1,8 @@
 # Top-level build: liblsdsort.so (the product) + the oracle checkers.
 # `python -c "import __graft_entry__ as g; g.build()"` runs the same commands.
 NVCC    ?= nvcc
+CXX     ?= g++
+CUDA_HOME ?= /usr/local/cuda
 GENCODE := -gencode arch=compute_100a,code=sm_100a
 NVFLAGS := -O3 -std=c++17 -lineinfo $(GENCODE) -Xcompiler -fPIC -Xcompiler -fvisibility=hidden --expt-relaxed-constexpr
 CSRC    := lsdradixsort_b200/csrc
@@ -9,8 +11,8 @@ SRCS    := api.cu sort.cu histogram.cu scan.cu onesweep_r1.cu onesweep_r2.cu one
 OBJS    := $(addprefix $(OBJDIR)/,$(SRCS:.cu=.o))
 LIB     := lsdradixsort_b200/liblsdsort.so
 
-.PHONY: all lib oracle clean
-all: lib oracle
+.PHONY: all lib oracle tools clean
+all: lib oracle tools
 
 lib: $(LIB)
 
@@ -20,6 +22,13 @@ $(OBJDIR)/%.o: $(CSRC)/%.cu $(wildcard $(CSRC)/*.cuh) $(wildcard $(CSRC)/*.h) in
 
 $(LIB): $(OBJS)
 	$(NVCC) $(GENCODE) -shared -o $@ $(OBJS)
+
+# lsd_bench: the reference's Test*/Benchmark* drivers over the C ABI (tools/lsd_bench.cpp)
+tools: build/lsd_bench
+build/lsd_bench: tools/lsd_bench.cpp include/lsdsort.h $(LIB)
+	@mkdir -p build
+	$(CXX) -O2 -std=c++17 -Iinclude -I$(CUDA_HOME)/include -o $@ $< -Llsdradixsort_b200 -llsdsort \
+	    -L$(CUDA_HOME)/lib64 -lcudart -Wl,-rpath,'$$ORIGIN/../lsdradixsort_b200'
 
 oracle:
 	$(MAKE) -C oracle oracle ref
