@@ -2,6 +2,7 @@
 // Entry 0 is the default; the others are reachable through `block` (threads per CTA, the
 // reference's B) and lsd_sort_options.variant (tuning sweeps from bench_tools/).
 #include "onesweep_lpc32.cuh"
+#include "onesweep_lpc2.cuh"
 #include "onesweep_lpcp.cuh"
 #include "onesweep_cpc.cuh"
 #include "onesweep_cpcp.cuh"
@@ -64,6 +65,16 @@ static const OnesweepLauncher kTable[] = {
     make_cpc_launcher<8, 64, 3, 4, 16>(),        // 52: CPC, look-back window 4, 32-bit Q rows
     make_cpc_launcher<8, 64, 3, 4, 48>(),        // 53: CPC, window 4, 32-bit Q rows, skewed reorder layout
     make_cpc_launcher<8, 64, 3, 4, 32>(),        // 54: CPC, window 4, skewed reorder layout
+    make_lpc2_launcher<8, 9, 29, 3, 4, 1>(),     // 55: two rank chains (packed half-word counters), no cluster
+    make_lpc2_launcher<8, 9, 29, 3, 4, 2>(),     // 56: two chains + one look-back record per cluster of 2 CTAs
+    make_lpc2_launcher<8, 9, 29, 3, 4, 4>(),     // 57: ... per cluster of 4
+    make_lpc2_launcher<8, 9, 29, 3, 4, 8>(),     // 58: ... per cluster of 8
+    make_lpc2_launcher<8, 9, 29, 3, 2, 4>(),     // 59: cluster of 4, look-back window 2
+    make_lpc2_launcher<8, 9, 29, 3, 8, 4>(),     // 60: cluster of 4, look-back window 8
+    make_lpc2_launcher<8, 9, 29, 3, 4, 1, false, 1>(),   // 61: two chains, no cluster, ld.global.cg polling
+    make_lpc2_launcher<8, 9, 29, 3, 8, 1, false, 1>(),   // 62: ... window 8
+    make_lpc2_launcher<8, 9, 29, 3, 16, 1, false, 1>(),  // 63: ... window 16
+    make_lpc2_launcher<8, 9, 29, 3, 8, 1>(),             // 64: two chains, strong polling, window 8
 };
 
 const OnesweepLauncher* onesweep_table_r8(int* count)
