@@ -46,7 +46,7 @@ enum lsd_status {
     LSD_ERR_INVALID_VALUE = 1,       /* bad r / block / bit_group / NULL pointer with n > 0 */
     LSD_ERR_WORKSPACE_TOO_SMALL = 2, /* ws_bytes < the matching *_workspace_bytes query */
     LSD_ERR_CUDA = 3,                /* a CUDA call or launch failed; see lsd_last_cuda_error */
-    LSD_ERR_UNSUPPORTED = 4,         /* size beyond what this build addresses */
+    LSD_ERR_UNSUPPORTED = 4,         /* size beyond what this build addresses, or a tuning variant without the requested form */
     LSD_ERR_ALIGNMENT = 5            /* key pointers must be 16-byte aligned, workspace 256-byte */
 };
 
@@ -112,7 +112,19 @@ typedef struct lsd_sort_options {
     uint32_t variant;       /* 0 = default kernel shape; other values select tuning variants */
     uint64_t debug_trace;   /* 0, or a device pointer to 16 uint64 per tile of the LAST pass: per-phase SM clocks
                                (tuning aid, only honoured by kernels that support it) */
+    uint32_t key_type;      /* enum lsd_key_type: how the 32-bit words are ORDERED (default LSD_KEY_U32, the reference) */
+    uint32_t reserved;      /* 0 */
 } lsd_sort_options;
+
+/* Key orderings beyond the reference's (its keys are uint32 only, LSDRadixSort.cu:839).  The 32-bit
+ * patterns are mapped to unsigned order by a bijection applied when the first executed pass reads the keys and undone
+ * when the last executed pass writes them (and inside the digit histogram), so it costs no extra pass over the data:
+ *   LSD_KEY_I32: two's-complement order (flip the sign bit);
+ *   LSD_KEY_F32: IEEE-754 total order: -NaN < -inf < ... < -0 < +0 < ... < +inf < +NaN (flip all bits of negatives,
+ *                the sign bit of the others) -- equal to `<` on floats wherever `<` decides.
+ * Supported by the default kernel shapes (variant 0, any r, any block) of lsd_sort_ex / lsd_sort_pairs / *_timed;
+ * other variants return LSD_ERR_UNSUPPORTED. */
+enum lsd_key_type { LSD_KEY_U32 = 0, LSD_KEY_I32 = 1, LSD_KEY_F32 = 2 };
 
 LSD_API size_t lsd_sort_workspace_bytes(uint64_t n, int r, int block);
 LSD_API size_t lsd_sort_workspace_bytes_ex(uint64_t n, int r, int block, const lsd_sort_options *opt);

@@ -21,6 +21,7 @@ LSD_ERR_WORKSPACE_TOO_SMALL = 2
 LSD_ERR_CUDA = 3
 LSD_ERR_UNSUPPORTED = 4
 LSD_ERR_ALIGNMENT = 5
+LSD_KEY_U32, LSD_KEY_I32, LSD_KEY_F32 = 0, 1, 2
 
 
 class LsdError(RuntimeError):
@@ -36,6 +37,8 @@ class SortOptions(C.Structure):
         ("disable_skip", C.c_uint32),
         ("variant", C.c_uint32),
         ("debug_trace", C.c_uint64),
+        ("key_type", C.c_uint32),
+        ("reserved", C.c_uint32),
     ]
 
 

@@ -19,28 +19,39 @@ import torch
 
 from . import _native as N
 
-_KEY_DTYPES = (torch.int32, torch.uint32)
+_KEY_DTYPES = (torch.int32, torch.uint32, torch.float32)
+_KEY_TYPES = {"u32": N.LSD_KEY_U32, "i32": N.LSD_KEY_I32, "f32": N.LSD_KEY_F32}
+
+
+def _typed_opts(keys: torch.Tensor, opts: dict) -> dict:
+    """float32 keys are ordered as floats unless the caller says otherwise; integer words keep the reference's order."""
+    if "key_type" in opts or keys.dtype != torch.float32:
+        return opts
+    return dict(opts, key_type="f32")
 
 
 def _stream_ptr(device: torch.device) -> int:
     return torch.cuda.current_stream(device).cuda_stream
 
 
-def _check_keys(t: torch.Tensor, what: str) -> None:
+def _check_keys(t: torch.Tensor, what: str, allow_float: bool = False) -> None:
     if not isinstance(t, torch.Tensor) or not t.is_cuda:
         raise TypeError(f"{what} must be a CUDA tensor (this library has no CPU path)")
-    if t.dtype not in _KEY_DTYPES:
-        raise TypeError(f"{what} must be int32/uint32, got {t.dtype}")
+    if t.dtype not in _KEY_DTYPES or (t.dtype == torch.float32 and not allow_float):
+        raise TypeError(f"{what} must be int32/uint32{'/float32' if allow_float else ''}, got {t.dtype}")
     if not t.is_contiguous() or t.dim() != 1:
         raise ValueError(f"{what} must be a contiguous 1-D tensor")
 
 
 def _options(portion_keys: int = 0, disable_skip: bool = False, variant: int = 0,
-             debug_trace: int = 0) -> Optional[N.SortOptions]:
-    if not (portion_keys or disable_skip or variant or debug_trace):
+             debug_trace: int = 0, key_type="u32") -> Optional[N.SortOptions]:
+    """``key_type``: how the 32-bit words are ordered -- "u32" (the reference's order, default), "i32" (signed) or
+    "f32" (IEEE total order); see lsd_key_type in include/lsdsort.h."""
+    kt = _KEY_TYPES[key_type] if isinstance(key_type, str) else int(key_type)
+    if not (portion_keys or disable_skip or variant or debug_trace or kt):
         return None
     return N.SortOptions(C.sizeof(N.SortOptions), int(portion_keys), int(bool(disable_skip)), int(variant),
-                         int(debug_trace))
+                         int(debug_trace), kt, 0)
 
 
 def set_device(index: int) -> None:
@@ -140,8 +151,9 @@ def GPULSDRadixSort(a: torch.Tensor, b: torch.Tensor, h: torch.Tensor, count: in
     """Reference-shaped call (.cu:839): sort ``a[:count]`` ascending using ``b`` as ping-pong space and
     ``h`` as scratch; the result is left in ``a``.  ``grid``, ``h_count``, ``d``, ``block_sums`` and
     ``block_sums_count`` of the reference are derived or unused and therefore not parameters here."""
-    _check_keys(a, "a")
-    _check_keys(b, "b")
+    _check_keys(a, "a", allow_float=True)
+    _check_keys(b, "b", allow_float=True)
+    opts = _typed_opts(a, opts)
     if b.numel() < count:
         raise ValueError("b must hold at least `count` keys")
     o = _options(**opts)
@@ -237,11 +249,11 @@ class Sorter:
 
     def sort_timed_(self, keys: torch.Tensor) -> list:
         """Sort and return per-stage device milliseconds [hist+plan, pass0.., copy-back] (synchronises)."""
-        _check_keys(keys, "keys")
+        _check_keys(keys, "keys", allow_float=True)
         stages = 32 // self.r + 2
         buf = (C.c_float * stages)()
         written = C.c_int(0)
-        o = _options(**self.opts)
+        o = _options(**_typed_opts(keys, self.opts))
         N.check(
             N.lib().lsd_sort_timed(keys.data_ptr(), self.scratch.data_ptr(), keys.numel(), self.r, self.block,
                                    self.workspace.data_ptr(), self.workspace.numel(), C.byref(o) if o else None,
@@ -276,14 +288,14 @@ class PairSorter:
         self.workspace = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=self.device)
 
     def _args(self, keys: torch.Tensor, vals: torch.Tensor):
-        _check_keys(keys, "keys")
-        _check_keys(vals, "vals")
+        _check_keys(keys, "keys", allow_float=True)
+        _check_keys(vals, "vals", allow_float=True)
         n = keys.numel()
         if vals.numel() != n:
             raise ValueError("keys and vals must have the same length")
         if n > self.max_n:
             raise ValueError("more pairs than this PairSorter's capacity")
-        o = _options(**self.opts)
+        o = _options(**_typed_opts(keys, self.opts))
         return (keys.data_ptr(), vals.data_ptr(), self.keys_scratch.data_ptr(), self.vals_scratch.data_ptr(), n, self.r,
                 self.block, self.workspace.data_ptr(), self.workspace.numel(), C.byref(o) if o else None,
                 _stream_ptr(keys.device))
@@ -304,14 +316,14 @@ class PairSorter:
 
 def sort_pairs_(keys: torch.Tensor, vals: torch.Tensor, r: int = 8, block: int = 0, **opts):
     """In-place key-value sort; allocates scratch for this one call."""
-    _check_keys(keys, "keys")
+    _check_keys(keys, "keys", allow_float=True)
     return PairSorter(keys.numel(), r, block, device=keys.device, **opts).sort_(keys, vals)
 
 
 def argsort(keys: torch.Tensor, r: int = 8, block: int = 0, **opts) -> torch.Tensor:
     """The stable sorting permutation of ``keys`` (int32 indices; ``keys`` is left untouched): values 0..n-1 carried
     through lsd_sort_pairs.  n < 2^31."""
-    _check_keys(keys, "keys")
+    _check_keys(keys, "keys", allow_float=True)
     n = keys.numel()
     idx = torch.arange(n, dtype=torch.int32, device=keys.device)
     sort_pairs_(keys.clone(), idx, r, block, **opts)
@@ -319,8 +331,9 @@ def argsort(keys: torch.Tensor, r: int = 8, block: int = 0, **opts) -> torch.Ten
 
 
 def sort_(keys: torch.Tensor, r: int = 8, block: int = 0, **opts) -> torch.Tensor:
-    """Sort ``keys`` in place, ascending as unsigned 32-bit; allocates scratch for this one call."""
-    _check_keys(keys, "keys")
+    """Sort ``keys`` in place; allocates scratch for this one call.  int32/uint32 tensors are ordered as UNSIGNED words
+    (the reference's order) unless ``key_type="i32"``; float32 tensors as floats (IEEE total order)."""
+    _check_keys(keys, "keys", allow_float=True)
     return Sorter(keys.numel(), r, block, device=keys.device, **opts).sort_(keys)
 
 
@@ -335,7 +348,7 @@ class HostSorter:
     def sort_(self, host_keys) -> None:
         """``host_keys``: pinned/pageable CPU torch tensor (int32/uint32) or numpy uint32 array, sorted in place."""
         if isinstance(host_keys, torch.Tensor):
-            if host_keys.is_cuda or host_keys.dtype not in _KEY_DTYPES or not host_keys.is_contiguous():
+            if host_keys.is_cuda or host_keys.dtype not in (torch.int32, torch.uint32) or not host_keys.is_contiguous():
                 raise TypeError("host_keys must be a contiguous CPU int32/uint32 tensor")
             ptr, n = host_keys.data_ptr(), host_keys.numel()
         else:

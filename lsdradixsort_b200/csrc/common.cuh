@@ -18,6 +18,25 @@ __host__ __device__ __forceinline__ uint32_t digit_of(uint32_t key, int shift)
     return (key >> shift) & ((1u << RB) - 1u);
 }
 
+// Order-preserving bijections between typed keys and unsigned order (lsd_key_type), branch-free and driven by two
+// masks: (flip, sign) = (0, 0) u32 -- identity; (0, 0x80000000) i32; (0x80000000, 0x80000000) f32.
+struct KeyXform {
+    uint32_t flip;  // bit whose value selects "flip everything"
+    uint32_t sign;  // bits that are always flipped
+};
+__host__ __device__ __forceinline__ KeyXform key_xform_of(uint32_t key_type)
+{
+    return KeyXform{key_type == 2u ? 0x80000000u : 0u, key_type != 0u ? 0x80000000u : 0u};
+}
+__host__ __device__ __forceinline__ uint32_t key_to_unsigned(uint32_t k, KeyXform x)
+{
+    return k ^ ((uint32_t)((int32_t)(k & x.flip) >> 31) | x.sign);
+}
+__host__ __device__ __forceinline__ uint32_t key_from_unsigned(uint32_t u, KeyXform x)
+{
+    return u ^ ((uint32_t)((int32_t)(~u & x.flip) >> 31) | x.sign);
+}
+
 __device__ __forceinline__ uint32_t lane_id()
 {
     uint32_t l;
@@ -97,7 +116,8 @@ int sm_count();          // cached multiprocessor count of the current device
 int smem_optin_bytes();  // cached max opt-in shared memory per block
 
 // ---- entry points implemented per translation unit (called by api.cu) ----------------
-int launch_digit_histograms(const uint32_t* keys, uint64_t n, int r, uint64_t* hist, cudaStream_t s);
+int launch_digit_histograms(const uint32_t* keys, uint64_t n, int r, uint64_t* hist, cudaStream_t s,
+                            uint32_t key_type = 0);
 int launch_top_digit_histogram(const uint32_t* keys, uint64_t n, int r, uint64_t* hist, cudaStream_t s);
 int launch_tile_histograms(const uint32_t* keys, uint64_t n, int r, int bit_group, int block, uint32_t* hist,
                            cudaStream_t s);

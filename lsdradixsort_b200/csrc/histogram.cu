@@ -25,11 +25,12 @@ namespace lsd {
 // -------------------------------------------------------------------------------------
 constexpr int kHistThreads = 1024;
 
-template <int RB, bool TOP_ONLY = false>
-__device__ __forceinline__ void hist_add_key(uint32_t* cnt_lane, uint32_t key)
+template <int RB, bool TOP_ONLY = false, bool TYPED = false>
+__device__ __forceinline__ void hist_add_key(uint32_t* cnt_lane, uint32_t key, KeyXform xf = KeyXform{0u, 0u})
 {
     constexpr int NP = 32 / RB;
     constexpr int H = 1 << RB;
+    if constexpr (TYPED) key = key_to_unsigned(key, xf);
 #pragma unroll
     for (int p = TOP_ONLY ? NP - 1 : 0; p < NP; ++p) {
         const uint32_t d = (key >> (p * RB)) & (H - 1);
@@ -37,9 +38,9 @@ __device__ __forceinline__ void hist_add_key(uint32_t* cnt_lane, uint32_t key)
     }
 }
 
-template <int RB, bool TOP_ONLY = false>
+template <int RB, bool TOP_ONLY = false, bool TYPED = false>
 __global__ void __launch_bounds__(kHistThreads, 1)
-digit_hist_kernel(const uint32_t* __restrict__ keys, uint64_t n, unsigned long long* __restrict__ hist)
+digit_hist_kernel(const uint32_t* __restrict__ keys, uint64_t n, unsigned long long* __restrict__ hist, KeyXform xf)
 {
     constexpr int NP = 32 / RB;
     constexpr int H = 1 << RB;
@@ -62,24 +63,24 @@ digit_hist_kernel(const uint32_t* __restrict__ keys, uint64_t n, unsigned long l
         const uint4 b = ld_stream_v4(keys + 4 * (i + stride));
         const uint4 c = ld_stream_v4(keys + 4 * (i + 2 * stride));
         const uint4 d = ld_stream_v4(keys + 4 * (i + 3 * stride));
-        hist_add_key<RB, TOP_ONLY>(cnt_lane, a.x); hist_add_key<RB, TOP_ONLY>(cnt_lane, a.y);
-        hist_add_key<RB, TOP_ONLY>(cnt_lane, a.z); hist_add_key<RB, TOP_ONLY>(cnt_lane, a.w);
-        hist_add_key<RB, TOP_ONLY>(cnt_lane, b.x); hist_add_key<RB, TOP_ONLY>(cnt_lane, b.y);
-        hist_add_key<RB, TOP_ONLY>(cnt_lane, b.z); hist_add_key<RB, TOP_ONLY>(cnt_lane, b.w);
-        hist_add_key<RB, TOP_ONLY>(cnt_lane, c.x); hist_add_key<RB, TOP_ONLY>(cnt_lane, c.y);
-        hist_add_key<RB, TOP_ONLY>(cnt_lane, c.z); hist_add_key<RB, TOP_ONLY>(cnt_lane, c.w);
-        hist_add_key<RB, TOP_ONLY>(cnt_lane, d.x); hist_add_key<RB, TOP_ONLY>(cnt_lane, d.y);
-        hist_add_key<RB, TOP_ONLY>(cnt_lane, d.z); hist_add_key<RB, TOP_ONLY>(cnt_lane, d.w);
+        hist_add_key<RB, TOP_ONLY, TYPED>(cnt_lane, a.x, xf); hist_add_key<RB, TOP_ONLY, TYPED>(cnt_lane, a.y, xf);
+        hist_add_key<RB, TOP_ONLY, TYPED>(cnt_lane, a.z, xf); hist_add_key<RB, TOP_ONLY, TYPED>(cnt_lane, a.w, xf);
+        hist_add_key<RB, TOP_ONLY, TYPED>(cnt_lane, b.x, xf); hist_add_key<RB, TOP_ONLY, TYPED>(cnt_lane, b.y, xf);
+        hist_add_key<RB, TOP_ONLY, TYPED>(cnt_lane, b.z, xf); hist_add_key<RB, TOP_ONLY, TYPED>(cnt_lane, b.w, xf);
+        hist_add_key<RB, TOP_ONLY, TYPED>(cnt_lane, c.x, xf); hist_add_key<RB, TOP_ONLY, TYPED>(cnt_lane, c.y, xf);
+        hist_add_key<RB, TOP_ONLY, TYPED>(cnt_lane, c.z, xf); hist_add_key<RB, TOP_ONLY, TYPED>(cnt_lane, c.w, xf);
+        hist_add_key<RB, TOP_ONLY, TYPED>(cnt_lane, d.x, xf); hist_add_key<RB, TOP_ONLY, TYPED>(cnt_lane, d.y, xf);
+        hist_add_key<RB, TOP_ONLY, TYPED>(cnt_lane, d.z, xf); hist_add_key<RB, TOP_ONLY, TYPED>(cnt_lane, d.w, xf);
     }
     for (; i < nvec; i += stride) {
         const uint4 a = ld_stream_v4(keys + 4 * i);
-        hist_add_key<RB, TOP_ONLY>(cnt_lane, a.x); hist_add_key<RB, TOP_ONLY>(cnt_lane, a.y);
-        hist_add_key<RB, TOP_ONLY>(cnt_lane, a.z); hist_add_key<RB, TOP_ONLY>(cnt_lane, a.w);
+        hist_add_key<RB, TOP_ONLY, TYPED>(cnt_lane, a.x, xf); hist_add_key<RB, TOP_ONLY, TYPED>(cnt_lane, a.y, xf);
+        hist_add_key<RB, TOP_ONLY, TYPED>(cnt_lane, a.z, xf); hist_add_key<RB, TOP_ONLY, TYPED>(cnt_lane, a.w, xf);
     }
     // ragged tail (n % 4 keys) -- block 0 only
     if (blockIdx.x == 0) {
         const uint64_t t = (nvec << 2) + tid;
-        if (t < n) hist_add_key<RB, TOP_ONLY>(cnt_lane, keys[t]);
+        if (t < n) hist_add_key<RB, TOP_ONLY, TYPED>(cnt_lane, keys[t], xf);
     }
     __syncthreads();
 
@@ -92,19 +93,20 @@ digit_hist_kernel(const uint32_t* __restrict__ keys, uint64_t n, unsigned long l
     }
 }
 
-template <int RB, bool TOP_ONLY = false>
-static int launch_digit_hist_t(const uint32_t* keys, uint64_t n, uint64_t* hist, cudaStream_t s)
+template <int RB, bool TOP_ONLY = false, bool TYPED = false>
+static int launch_digit_hist_t(const uint32_t* keys, uint64_t n, uint64_t* hist, cudaStream_t s, uint32_t key_type = 0)
 {
     constexpr int ROWS = (32 / RB) << RB;
     const size_t smem = (size_t)ROWS * 32 * sizeof(uint32_t);
     LSD_CUDA_TRY(cudaMemsetAsync(hist, 0, (size_t)ROWS * sizeof(uint64_t), s));
     if (n == 0) return LSD_OK;
-    LSD_CUDA_TRY(cudaFuncSetAttribute(digit_hist_kernel<RB, TOP_ONLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    LSD_CUDA_TRY(cudaFuncSetAttribute(digit_hist_kernel<RB, TOP_ONLY, TYPED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // one CTA per SM, but never more CTAs than there are 16 KiB slices of input
     const uint64_t slices = ((n >> 2) + kHistThreads - 1) / kHistThreads;
     int grid = sm_count();
     if ((uint64_t)grid > slices) grid = (int)(slices ? slices : 1);
-    digit_hist_kernel<RB, TOP_ONLY><<<grid, kHistThreads, smem, s>>>(keys, n, reinterpret_cast<unsigned long long*>(hist));
+    digit_hist_kernel<RB, TOP_ONLY, TYPED><<<grid, kHistThreads, smem, s>>>(keys, n, reinterpret_cast<unsigned long long*>(hist),
+                                                                            key_xform_of(key_type));
     LSD_LAUNCH_CHECK();
     return LSD_OK;
 }
@@ -122,8 +124,17 @@ int launch_top_digit_histogram(const uint32_t* keys, uint64_t n, int r, uint64_t
     return LSD_ERR_INVALID_VALUE;
 }
 
-int launch_digit_histograms(const uint32_t* keys, uint64_t n, int r, uint64_t* hist, cudaStream_t s)
+int launch_digit_histograms(const uint32_t* keys, uint64_t n, int r, uint64_t* hist, cudaStream_t s, uint32_t key_type)
 {
+    if (key_type != 0) {  // typed keys: histogram of the keys' unsigned images
+        switch (r) {
+            case 1: return launch_digit_hist_t<1, false, true>(keys, n, hist, s, key_type);
+            case 2: return launch_digit_hist_t<2, false, true>(keys, n, hist, s, key_type);
+            case 4: return launch_digit_hist_t<4, false, true>(keys, n, hist, s, key_type);
+            case 8: return launch_digit_hist_t<8, false, true>(keys, n, hist, s, key_type);
+        }
+        return LSD_ERR_INVALID_VALUE;
+    }
     switch (r) {
         case 1: return launch_digit_hist_t<1>(keys, n, hist, s);
         case 2: return launch_digit_hist_t<2>(keys, n, hist, s);

@@ -42,7 +42,9 @@ struct SortPlan {
     uint32_t src_is_scratch[kMaxPasses];
     uint32_t result_in_scratch;
     uint32_t executed_passes;
-    uint32_t pad[62];
+    uint32_t first_pass;  // first / last executed pass (typed keys are mapped to unsigned order on the way in and back
+    uint32_t last_pass;   // on the way out); kMaxPasses when nothing runs
+    uint32_t pad[60];
 };
 
 struct PassArgs {
@@ -63,9 +65,21 @@ struct PassArgs {
     const uint32_t* dst_seg;    // peer-scatter mode only: [H] first | last << 16 bucket of the bucket's segment, or nullptr
     uint32_t* vals;             // pairs mode only: the caller's value buffer (travels with `keys`)
     uint32_t* vals_scratch;     // pairs mode only: ping-pong buffer of the values (travels with `scratch`)
+    uint32_t key_type;          // lsd_key_type; non-zero only with the typed-key kernels (OnesweepLauncher.launch_typed)
 };
 
-constexpr int kPassPlain = 0, kPassPeer = 1, kPassPairs = 2;
+// The key mapping a pass applies when it reads / writes keys: identity unless the keys are typed and this is the first /
+// last executed pass.
+__device__ __forceinline__ KeyXform pass_xform_in(const PassArgs& a)
+{
+    return key_xform_of((a.key_type != 0u && a.plan->first_pass == (uint32_t)a.pass) ? a.key_type : 0u);
+}
+__device__ __forceinline__ KeyXform pass_xform_out(const PassArgs& a)
+{
+    return key_xform_of((a.key_type != 0u && a.plan->last_pass == (uint32_t)a.pass) ? a.key_type : 0u);
+}
+
+constexpr int kPassPlain = 0, kPassPeer = 1, kPassPairs = 2, kPassTyped = 3, kPassPairsTyped = 4;
 
 enum MatchMode { kMatchBallot = 0, kMatchHw = 1 };
 
@@ -98,7 +112,7 @@ struct OnesweepShape {
     static constexpr uint32_t PORTION_MAX = (uint32_t)((((1u << 30) - 1u) / TILE) * TILE);
 };
 
-template <int RB, int THREADS, int ITEMS, int MODE, bool PAIRS = false>
+template <int RB, int THREADS, int ITEMS, int MODE, bool PAIRS = false, bool TYPED = false>
 __global__ void __launch_bounds__(THREADS)
 onesweep_kernel(const PassArgs a)
 {
@@ -142,6 +156,12 @@ onesweep_kernel(const PassArgs a)
 #pragma unroll
             for (int i = 0; i < ITEMS; ++i)
                 key[i] = (off + i * 32u < valid) ? ld_stream_u32(src + i * 32) : 0xFFFFFFFFu;  // pads sort last
+        }
+        if constexpr (TYPED) {  // typed keys enter unsigned order in the first executed pass (pads stay last)
+            const KeyXform xin = pass_xform_in(a);
+#pragma unroll
+            for (int i = 0; i < ITEMS; ++i)
+                if (valid == (uint32_t)TILE || off + i * 32u < valid) key[i] = key_to_unsigned(key[i], xin);
         }
     }
 
@@ -253,6 +273,7 @@ onesweep_kernel(const PassArgs a)
     __syncthreads();
 
     // ---- 6. stream the reorder buffer out, coalesced per bucket ----
+    const KeyXform xout = TYPED ? pass_xform_out(a) : KeyXform{0u, 0u};  // typed keys leave unsigned order in the last executed pass
     if constexpr (PAIRS) {
         // keys out, remembering the digit of every position this thread copies: the value of the key at tile
         // position p goes to the same global index.  Then the values take the keys' route through the reorder
@@ -266,7 +287,7 @@ onesweep_kernel(const PassArgs a)
             if (p < valid) {
                 const uint32_t k = s_keys[p];
                 d = digit_of<RB>(k, a.shift);
-                out[s_gbase[d] + p] = k;
+                out[s_gbase[d] + p] = (TYPED ? key_from_unsigned(k, xout) : k);
             }
             if (i & 3) dpk[i >> 2] |= d << (8 * (i & 3)); else dpk[i >> 2] = d;
         }
@@ -295,7 +316,7 @@ onesweep_kernel(const PassArgs a)
         for (int i = 0; i < ITEMS; ++i) {
             const uint32_t p = i * THREADS + tid;
             const uint32_t k = s_keys[p];
-            out[s_gbase[digit_of<RB>(k, a.shift)] + p] = k;
+            out[s_gbase[digit_of<RB>(k, a.shift)] + p] = (TYPED ? key_from_unsigned(k, xout) : k);
         }
     } else {
 #pragma unroll
@@ -303,7 +324,7 @@ onesweep_kernel(const PassArgs a)
             const uint32_t p = i * THREADS + tid;
             if (p < valid) {
                 const uint32_t k = s_keys[p];
-                out[s_gbase[digit_of<RB>(k, a.shift)] + p] = k;
+                out[s_gbase[digit_of<RB>(k, a.shift)] + p] = (TYPED ? key_from_unsigned(k, xout) : k);
             }
         }
     }
@@ -321,20 +342,22 @@ struct OnesweepLauncher {
     int (*launch)(const PassArgs& a, cudaStream_t s);
     int (*launch_peer)(const PassArgs& a, cudaStream_t s);  // bucket-pointer scatter (multi-GPU exchange), or nullptr
     int (*launch_pairs)(const PassArgs& a, cudaStream_t s);  // key-value pass, or nullptr
+    int (*launch_typed)(const PassArgs& a, cudaStream_t s);        // plain pass that maps typed keys (i32 / f32), or nullptr
+    int (*launch_pairs_typed)(const PassArgs& a, cudaStream_t s);  // key-value pass that maps typed keys, or nullptr
 };
 
-template <int RB, int THREADS, int ITEMS, int MODE, bool PAIRS = false>
+template <int RB, int THREADS, int ITEMS, int MODE, bool PAIRS = false, bool TYPED = false>
 int onesweep_launch(const PassArgs& a, cudaStream_t s)
 {
     using S = OnesweepShape<RB, THREADS, ITEMS>;
-    LSD_CUDA_TRY(cudaFuncSetAttribute(onesweep_kernel<RB, THREADS, ITEMS, MODE, PAIRS>,
+    LSD_CUDA_TRY(cudaFuncSetAttribute(onesweep_kernel<RB, THREADS, ITEMS, MODE, PAIRS, TYPED>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::SMEM_BYTES));
-    onesweep_kernel<RB, THREADS, ITEMS, MODE, PAIRS><<<a.tiles, THREADS, S::SMEM_BYTES, s>>>(a);
+    onesweep_kernel<RB, THREADS, ITEMS, MODE, PAIRS, TYPED><<<a.tiles, THREADS, S::SMEM_BYTES, s>>>(a);
     LSD_LAUNCH_CHECK();
     return LSD_OK;
 }
 
-// WITH_PAIRS: also instantiate the key-value form of the kernel (the default shape of every radix has it).
+// WITH_PAIRS: also instantiate the key-value and the typed-key (i32 / f32) forms of the kernel.
 template <int RB, int THREADS, int ITEMS, int MODE, bool WITH_PAIRS = false>
 constexpr OnesweepLauncher make_launcher()
 {
@@ -342,10 +365,12 @@ constexpr OnesweepLauncher make_launcher()
     if constexpr (WITH_PAIRS)
         return OnesweepLauncher{RB, THREADS, ITEMS, MODE, (uint32_t)S::TILE, S::PORTION_MAX, S::SMEM_BYTES,
                                 &onesweep_launch<RB, THREADS, ITEMS, MODE>, nullptr,
-                                &onesweep_launch<RB, THREADS, ITEMS, MODE, true>};
+                                &onesweep_launch<RB, THREADS, ITEMS, MODE, true>,
+                                &onesweep_launch<RB, THREADS, ITEMS, MODE, false, true>,
+                                &onesweep_launch<RB, THREADS, ITEMS, MODE, true, true>};
     else
         return OnesweepLauncher{RB, THREADS, ITEMS, MODE, (uint32_t)S::TILE, S::PORTION_MAX, S::SMEM_BYTES,
-                                &onesweep_launch<RB, THREADS, ITEMS, MODE>, nullptr, nullptr};
+                                &onesweep_launch<RB, THREADS, ITEMS, MODE>, nullptr, nullptr, nullptr, nullptr};
 }
 
 // Tables defined in onesweep_r{1,2,4,8}.cu.  Entry 0 of each table is the default shape.

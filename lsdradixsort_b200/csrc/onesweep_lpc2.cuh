@@ -433,10 +433,10 @@ constexpr OnesweepLauncher make_lpc2_launcher()
         return OnesweepLauncher{RB, S_::THREADS, ITEMS, kModeLpc2, (uint32_t)S_::TILE, S_::PORTION_MAX, S_::SMEM_BYTES,
                                 &onesweep_lpc2_launch<RB, WARPS, ITEMS, MINB, LB, CL, POLL>,
                                 &onesweep_lpc32_launch<RB, WARPS, ITEMS, MINB, 4, 0, kPassPeer, false>,
-                                &onesweep_lpc32_launch<RB, WARPS, ITEMS, MINB, 4, 0, kPassPairs, false>};
+                                &onesweep_lpc32_launch<RB, WARPS, ITEMS, MINB, 4, 0, kPassPairs, false>, nullptr, nullptr};
     else
         return OnesweepLauncher{RB, S_::THREADS, ITEMS, kModeLpc2, (uint32_t)S_::TILE, S_::PORTION_MAX, S_::SMEM_BYTES,
-                                &onesweep_lpc2_launch<RB, WARPS, ITEMS, MINB, LB, CL, POLL>, nullptr, nullptr};
+                                &onesweep_lpc2_launch<RB, WARPS, ITEMS, MINB, LB, CL, POLL>, nullptr, nullptr, nullptr, nullptr};
 }
 
 }  // namespace lsd

@@ -65,7 +65,8 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
 onesweep_lpc32_kernel(const PassArgs a)
 {
     constexpr bool PEER = MODE == kPassPeer;    // bucket-pointer scatter (multi-GPU exchange)
-    constexpr bool PAIRS = MODE == kPassPairs;  // a 32-bit value travels with every key
+    constexpr bool PAIRS = MODE == kPassPairs || MODE == kPassPairsTyped;  // a 32-bit value travels with every key
+    constexpr bool TYPED = MODE == kPassTyped || MODE == kPassPairsTyped;  // i32 / f32 keys: mapped to unsigned order
     using S_ = Lpc32Shape<RB, WARPS, ITEMS>;
     constexpr int H = S_::H, THREADS = S_::THREADS, S = S_::S, TILE = S_::TILE;
     constexpr int SW = S_::SW, GPW = S_::GPW, LBT = S_::LBT, LBW = S_::LBW;
@@ -153,7 +154,9 @@ onesweep_lpc32_kernel(const PassArgs a)
     if (valid == (uint32_t)TILE) {
         mbar_wait(s_bar, 0);
     } else {
-        for (uint32_t p = tid; p < (uint32_t)TILE; p += THREADS) s_keys[p] = p < valid ? in[tile_base + p] : 0xFFFFFFFFu;
+        // pads are the pre-image of 0xFFFFFFFF under this pass's input mapping (identity unless the keys are typed)
+        const uint32_t pad_key = TYPED ? key_from_unsigned(0xFFFFFFFFu, pass_xform_in(a)) : 0xFFFFFFFFu;
+        for (uint32_t p = tid; p < (uint32_t)TILE; p += THREADS) s_keys[p] = p < valid ? in[tile_base + p] : pad_key;
         __syncthreads();
     }
     if (warp == 0) LSD_TRACE(1);  // tile landed
@@ -164,6 +167,11 @@ onesweep_lpc32_kernel(const PassArgs a)
         const uint32_t* src = s_keys + lane * S + warp * ITEMS;
 #pragma unroll
         for (int i = 0; i < ITEMS; ++i) key[i] = src[i];
+    }
+    if constexpr (TYPED) {  // typed keys (i32 / f32) enter unsigned order when the first executed pass reads them
+        const KeyXform xin = pass_xform_in(a);
+#pragma unroll
+        for (int i = 0; i < ITEMS; ++i) key[i] = key_to_unsigned(key[i], xin);
     }
     char* mat_bytes = reinterpret_cast<char*>(s_mat);
     const uint32_t lane4 = lane << 2;
@@ -406,6 +414,9 @@ onesweep_lpc32_kernel(const PassArgs a)
     if (warp == 0) LSD_TRACE(11);  // final barrier passed
 
     // ---- 3. stream the reorder buffer out, coalesced per bucket ----
+    // typed keys leave unsigned order when the last executed pass writes them (uniform over the grid)
+    const bool typed_out = TYPED && a.plan->last_pass == (uint32_t)a.pass;
+    const KeyXform xout = key_xform_of(typed_out ? a.key_type : 0u);
     if constexpr (PEER) {
         // one loop per destination segment, warps aligned to the 128-byte lines of the DESTINATION: every store of a
         // long run is one full line (NVLink packets carry whole lines, no partial sectors)
@@ -434,7 +445,7 @@ onesweep_lpc32_kernel(const PassArgs a)
             if (p < valid) {
                 const uint32_t k = s_keys[p];
                 d = (k >> SHIFT) & (H - 1);
-                out[s_gbase[d] + p] = k;
+                out[s_gbase[d] + p] = TYPED ? key_from_unsigned(k, xout) : k;
             }
             if (i & 3) dpk[i >> 2] |= d << (8 * (i & 3)); else dpk[i >> 2] = d;
         }
@@ -476,7 +487,7 @@ onesweep_lpc32_kernel(const PassArgs a)
             const uint32_t d = (dpk[i >> 2] >> (8 * (i & 3))) & 0xFFu;
             if (p < valid) vout[s_gbase[d] + p] = s_keys[p];
         }
-    } else if (valid == (uint32_t)TILE) {
+    } else if (valid == (uint32_t)TILE && !typed_out) {
 #pragma unroll
         for (int i = 0; i < ITEMS; ++i) {
             const uint32_t p = i * THREADS + tid;
@@ -486,7 +497,7 @@ onesweep_lpc32_kernel(const PassArgs a)
     } else {
         for (uint32_t p = tid; p < valid; p += THREADS) {
             const uint32_t k = s_keys[p];
-            out[s_gbase[(k >> SHIFT) & (H - 1)] + p] = k;
+            out[s_gbase[(k >> SHIFT) & (H - 1)] + p] = TYPED ? key_from_unsigned(k, xout) : k;
         }
     }
     if (warp == 0) LSD_TRACE(12);  // warp 0 issued its stores
@@ -528,10 +539,13 @@ constexpr OnesweepLauncher make_lpc32_launcher()
         return OnesweepLauncher{RB, S_::THREADS, ITEMS, kModeLpc32, (uint32_t)S_::TILE, S_::PORTION_MAX, S_::SMEM_BYTES,
                                 &onesweep_lpc32_launch<RB, WARPS, ITEMS, MINB, LB, CLR, kPassPlain, SP>,
                                 &onesweep_lpc32_launch<RB, WARPS, ITEMS, MINB, LB, CLR, kPassPeer, SP>,
-                                &onesweep_lpc32_launch<RB, WARPS, ITEMS, MINB, LB, CLR, kPassPairs, SP>};
+                                &onesweep_lpc32_launch<RB, WARPS, ITEMS, MINB, LB, CLR, kPassPairs, SP>,
+                                &onesweep_lpc32_launch<RB, WARPS, ITEMS, MINB, LB, CLR, kPassTyped, SP>,
+                                &onesweep_lpc32_launch<RB, WARPS, ITEMS, MINB, LB, CLR, kPassPairsTyped, SP>};
     else
         return OnesweepLauncher{RB, S_::THREADS, ITEMS, kModeLpc32, (uint32_t)S_::TILE, S_::PORTION_MAX, S_::SMEM_BYTES,
-                                &onesweep_lpc32_launch<RB, WARPS, ITEMS, MINB, LB, CLR, kPassPlain, SP>, nullptr, nullptr};
+                                &onesweep_lpc32_launch<RB, WARPS, ITEMS, MINB, LB, CLR, kPassPlain, SP>, nullptr, nullptr, nullptr,
+                                nullptr};
 }
 
 }  // namespace lsd

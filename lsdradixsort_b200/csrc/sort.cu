@@ -29,7 +29,7 @@ plan_kernel(const uint64_t* __restrict__ hist, uint64_t* __restrict__ bases, Sor
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     if (tid == 0) s_parity = 0;
     __syncthreads();
-    uint32_t executed = 0;
+    uint32_t executed = 0, first = kMaxPasses, last = kMaxPasses;
     for (int p = 0; p < passes; ++p) {
         const uint64_t v = (int)tid < H ? hist[p * H + tid] : 0ull;
         const int full = __syncthreads_or(v == n);
@@ -48,13 +48,20 @@ plan_kernel(const uint64_t* __restrict__ hist, uint64_t* __restrict__ bases, Sor
             const uint32_t skip = (full && !disable_skip) ? 1u : 0u;
             plan->skip[p] = skip;
             plan->src_is_scratch[p] = s_parity;
-            if (!skip) { s_parity ^= 1u; ++executed; }
+            if (!skip) {
+                s_parity ^= 1u;
+                ++executed;
+                if (first == (uint32_t)kMaxPasses) first = (uint32_t)p;
+                last = (uint32_t)p;
+            }
         }
         __syncthreads();
     }
     if (tid == 0) {
         plan->result_in_scratch = s_parity;
         plan->executed_passes = executed;
+        plan->first_pass = first;
+        plan->last_pass = last;
     }
 }
 
@@ -89,18 +96,24 @@ static const OnesweepLauncher* table_for(int r, int* count)
     return nullptr;
 }
 
-const OnesweepLauncher* select_launcher(int r, int block, uint32_t variant, bool pairs)
+// the launch entry a sort of this flavour needs (nullptr: this shape does not have it)
+static int (*pass_fn(const OnesweepLauncher& k, bool pairs, bool typed))(const PassArgs&, cudaStream_t)
+{
+    return typed ? (pairs ? k.launch_pairs_typed : k.launch_typed) : (pairs ? k.launch_pairs : k.launch);
+}
+
+const OnesweepLauncher* select_launcher(int r, int block, uint32_t variant, bool pairs, bool typed)
 {
     int count = 0;
     const OnesweepLauncher* t = table_for(r, &count);
     if (!t) return nullptr;
-    if (variant != 0) return (variant < (uint32_t)count && (!pairs || t[variant].launch_pairs)) ? &t[variant] : nullptr;
-    if (block <= 0) return &t[0];  // entry 0 of every table has the key-value form
+    if (variant != 0) return variant < (uint32_t)count ? &t[variant] : nullptr;
+    if (block <= 0) return &t[0];  // entry 0 of every table has every form
     // `block` is the reference's threads-per-block knob: pick the warp-multisplit shape with exactly that many
     // threads if there is one, else the shape (of any family) whose CTA size is closest.
     const OnesweepLauncher* best = nullptr;
     for (int i = 0; i < count; ++i) {
-        if (pairs && !t[i].launch_pairs) continue;
+        if (!pass_fn(t[i], pairs, typed)) continue;
         if (t[i].mode == kMatchBallot && t[i].threads == block) return &t[i];
         if (!best || std::abs(t[i].threads - block) < std::abs(best->threads - block)) best = &t[i];
     }
@@ -115,8 +128,11 @@ int make_layout(uint64_t n, int r, int block, const lsd_sort_options* opt, SortL
     if (block < 0 || block > 1024) return LSD_ERR_INVALID_VALUE;
     if (n >= (1ull << 32)) return LSD_ERR_UNSUPPORTED;  // 32-bit scatter indices in this build
     const uint32_t variant = opt ? opt->variant : 0u;
-    const OnesweepLauncher* k = select_launcher(r, block, variant, pairs);
+    const uint32_t key_type = opt ? opt->key_type : 0u;
+    if (key_type > LSD_KEY_F32) return LSD_ERR_INVALID_VALUE;
+    const OnesweepLauncher* k = select_launcher(r, block, variant, pairs, key_type != 0u);
     if (!k) return LSD_ERR_INVALID_VALUE;
+    if (!pass_fn(*k, pairs, key_type != 0u)) return LSD_ERR_UNSUPPORTED;  // this tuning variant lacks the requested form
     L->k = k;
     L->passes = 32 / r;
     L->H = 1 << r;
@@ -161,6 +177,7 @@ int sort_enqueue(uint32_t* keys, uint32_t* scratch, uint64_t n, int r, int block
     if (ws_bytes < L.total_bytes) return LSD_ERR_WORKSPACE_TOO_SMALL;
     if (!aligned_to(keys, 16) || !aligned_to(scratch, 16) || !aligned_to(ws, 256)) return LSD_ERR_ALIGNMENT;
     if (pairs && (!aligned_to(vals, 16) || !aligned_to(vals_scratch, 16))) return LSD_ERR_ALIGNMENT;
+    const uint32_t key_type = opt ? opt->key_type : 0u;
 
     char* w = static_cast<char*>(ws);
     SortPlan* plan = reinterpret_cast<SortPlan*>(w + L.off_plan);
@@ -172,7 +189,7 @@ int sort_enqueue(uint32_t* keys, uint32_t* scratch, uint64_t n, int r, int block
     int ev = 0, nl = 0;
     if (events) LSD_CUDA_TRY(cudaEventRecord(events[ev++], s));
     LSD_CUDA_TRY(cudaMemsetAsync(ws, 0, L.total_bytes, s));
-    int rc = launch_digit_histograms(keys, n, r, hist, s);
+    int rc = launch_digit_histograms(keys, n, r, hist, s, key_type);
     if (rc != LSD_OK) return rc;
     ++nl;
     plan_kernel<<<1, kPlanThreads, 0, s>>>(hist, bases, plan, n, L.passes, L.H, opt ? (int)opt->disable_skip : 0);
@@ -204,7 +221,8 @@ int sort_enqueue(uint32_t* keys, uint32_t* scratch, uint64_t n, int r, int block
             a.dst_seg = nullptr;
             a.vals = vals;
             a.vals_scratch = vals_scratch;
-            rc = pairs ? L.k->launch_pairs(a, s) : L.k->launch(a, s);
+            a.key_type = key_type;
+            rc = pass_fn(*L.k, pairs, key_type != 0u)(a, s);
             if (rc != LSD_OK) return rc;
             ++nl;
             lb += (size_t)a.tiles * L.H;
@@ -314,6 +332,7 @@ int pass_enqueue(const uint32_t* in, uint32_t* out, uint64_t n, int r, int bit_g
         a.dst_seg = dst_seg;
         a.vals = nullptr;
         a.vals_scratch = nullptr;
+        a.key_type = 0;
         rc = peer ? L.k->launch_peer(a, s) : L.k->launch(a, s);
         if (rc != LSD_OK) return rc;
         lb += (size_t)a.tiles * L.H;

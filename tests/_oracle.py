@@ -123,3 +123,34 @@ def digit_histograms(keys: np.ndarray, r: int) -> np.ndarray:
     h = np.zeros((32 // r) * (1 << r), dtype=np.uint64)
     oracle().lsd_oracle_digit_histograms(a, a.size, r, h)
     return h.reshape(32 // r, 1 << r)
+
+
+# ---- typed keys (lsd_key_type): the reference's sort applied to the keys' unsigned images ----------------------
+def to_unsigned(bits: np.ndarray, key_type: str) -> np.ndarray:
+    """Order-preserving bijection onto unsigned order: i32 flips the sign bit, f32 flips all bits of negatives and the
+    sign bit of the others (IEEE total order).  Plain numpy restatement of key_to_unsigned in csrc/common.cuh."""
+    b = np.ascontiguousarray(bits).view(np.uint32)
+    if key_type == "u32":
+        return b.copy()
+    if key_type == "i32":
+        return b ^ np.uint32(0x80000000)
+    assert key_type == "f32"
+    return np.where(b >> np.uint32(31), ~b, b ^ np.uint32(0x80000000)).astype(np.uint32)
+
+
+def from_unsigned(u: np.ndarray, key_type: str) -> np.ndarray:
+    if key_type == "u32":
+        return u.copy()
+    if key_type == "i32":
+        return u ^ np.uint32(0x80000000)
+    return np.where(u >> np.uint32(31), u ^ np.uint32(0x80000000), ~u).astype(np.uint32)
+
+
+def sort_typed(bits: np.ndarray, key_type: str, r: int = 8) -> np.ndarray:
+    """Sorted 32-bit patterns in `key_type` order: LSDRadixSort (.cu:62-69) on the unsigned images, mapped back."""
+    return from_unsigned(sort(to_unsigned(bits, key_type), r), key_type)
+
+
+def sort_pairs_typed(bits: np.ndarray, vals: np.ndarray, key_type: str, r: int = 8):
+    k, v = sort_pairs(to_unsigned(bits, key_type), vals, r)
+    return from_unsigned(k, key_type), v

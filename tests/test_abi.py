@@ -78,9 +78,9 @@ def test_sort_argument_validation_order():
     assert lib.lsd_sort(0x1000, 0x2000, 16, 8, 0, 0x3000, 16, None) == N.LSD_ERR_WORKSPACE_TOO_SMALL
     assert lib.lsd_sort(0x1004, 0x2000, 16, 8, 0, 0x3000, 1 << 30, None) == N.LSD_ERR_ALIGNMENT
     assert lib.lsd_sort(0x1000, 0x2000, 1 << 33, 8, 0, 0x3000, 1 << 40, None) == N.LSD_ERR_UNSUPPORTED
-    bad = N.SortOptions(4, 0, 0, 0, 0)  # wrong struct_bytes
+    bad = N.SortOptions(4, 0, 0, 0, 0, 0, 0)  # wrong struct_bytes
     assert lib.lsd_sort_ex(0x1000, 0x2000, 16, 8, 0, 0x3000, 1 << 30, C.byref(bad), None) == N.LSD_ERR_INVALID_VALUE
-    unknown_variant = N.SortOptions(C.sizeof(N.SortOptions), 0, 0, 999, 0)
+    unknown_variant = N.SortOptions(C.sizeof(N.SortOptions), 0, 0, 999, 0, 0, 0)
     assert lib.lsd_sort_ex(0x1000, 0x2000, 16, 8, 0, 0x3000, 1 << 30, C.byref(unknown_variant), None) == N.LSD_ERR_INVALID_VALUE
 
 

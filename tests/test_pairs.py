@@ -58,9 +58,9 @@ def test_pairs_abi_validation_without_cuda():
         for block in (128, 256, 512, 1024):
             assert lib.lsd_sort_pairs_workspace_bytes(1 << 20, r, block, None) > 0
     # a tuning variant that has no key-value form is refused, not silently replaced
-    no_pairs = N.SortOptions(C.sizeof(N.SortOptions), 0, 0, 32, 0)
+    no_pairs = N.SortOptions(C.sizeof(N.SortOptions), 0, 0, 32, 0, 0, 0)
     assert lib.lsd_sort_pairs_workspace_bytes(1 << 20, 8, 0, C.byref(no_pairs)) == 0
-    assert lib.lsd_sort_pairs(0x1000, 0x2000, 0x3000, 0x4000, 16, 8, 0, 0x5000, big, C.byref(no_pairs), None) == N.LSD_ERR_INVALID_VALUE
+    assert lib.lsd_sort_pairs(0x1000, 0x2000, 0x3000, 0x4000, 16, 8, 0, 0x5000, big, C.byref(no_pairs), None) == N.LSD_ERR_UNSUPPORTED
 
 
 # ------------------------------------------------------------------ GPU: parity through the C ABI
