@@ -67,34 +67,96 @@ def workload(args):
 # helpers
 # ----------------------------------------------------------------------------------------------
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+    """Samples SM clocks / clock-event (throttle) reasons WHILE the timed region runs.
+
+    The timed region of the default run is ~50 ms (10 sorts of 2^28 keys), shorter than one `nvidia-smi -lms` period,
+    so the samples come from NVML directly (nvidia_ml_py, a thread polling every ~2 ms; the main thread only enqueues
+    work and then blocks in a synchronise, which releases the GIL).  Falls back to an `nvidia-smi -lms` child started
+    before the warm-up when NVML cannot be loaded."""
 
     FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
               "clocks_event_reasons.sw_power_cap")
+    REASON_BITS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap"))
 
     def __init__(self, gpu_index: int):
         self.gpu = gpu_index
         self.proc = None
         self.lines = []
+        self.nvml = None
+        self.handle = None
+        self.samples = []   # (sm_mhz, reasons bitmask)
+        self.sm_max = None
+        self._run = False
+        self._thread = None
+        try:
+            import pynvml
+            import torch
 
-    def start(self):
+            pynvml.nvmlInit()
+            try:
+                uuid = str(torch.cuda.get_device_properties(gpu_index).uuid)
+                self.handle = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+            except Exception:  # noqa: BLE001
+                self.handle = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+        except Exception:  # noqa: BLE001
+            self.nvml = None
+
+    def prestart(self):
+        """nvidia-smi fallback only: the child needs ~100 ms before its first line, so start it before the warm-up."""
+        if self.nvml is not None:
+            return
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100",
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "20",
                  "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except OSError:
             self.proc = None
+
+    def start(self):
+        if self.nvml is not None:
+            self._run = True
+            self._thread = threading.Thread(target=self._poll, daemon=True)
+            self._thread.start()
+        else:
+            self.lines.clear()  # keep only what arrives during the timed region
+
+    def _poll(self):
+        n = self.nvml
+        while self._run:
+            try:
+                mhz = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+                try:
+                    bits = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+                except Exception:  # noqa: BLE001
+                    bits = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+                self.samples.append((mhz, bits))
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(0.002)
 
     def _pump(self):
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
     def stop(self) -> dict:
+        if self.nvml is not None:
+            self._run = False
+            if self._thread is not None:
+                self._thread.join(timeout=1.0)
+            sm = sorted(x[0] for x in self.samples)
+            reasons = set()
+            for _, bits in self.samples:
+                for mask, name in self.REASON_BITS:
+                    if bits & mask:
+                        reasons.add(name)
+            return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.sm_max, "reasons": sorted(reasons),
+                    "samples": len(sm), "source": "NVML polled every ~2 ms during the timed region"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
         self.proc.terminate()
         sm, smax, reasons = [], [], set()
         for ln in self.lines:
@@ -111,7 +173,7 @@ class ClockSampler:
                     reasons.add(name)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi -lms 20 during the timed region"}
 
 
 def measured_peak():
@@ -248,11 +310,13 @@ def run_ours(args):
 
     ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.prestart()
     for _ in range(args.warmup):
         work.copy_(src)
         step()
     barrier()
-    sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     stats = None

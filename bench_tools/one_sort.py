@@ -15,6 +15,7 @@ ap.add_argument("--variant", type=int, default=0)
 ap.add_argument("--reps", type=int, default=2)
 ap.add_argument("--r", type=int, default=8)
 ap.add_argument("--scan", action="store_true", help="also run prefix_sum once")
+ap.add_argument("--pairs", action="store_true", help="also run one key-value sort (lsd_sort_pairs)")
 args = ap.parse_args()
 n = 1 << args.log2n
 g = torch.Generator(device="cuda").manual_seed(0)
@@ -24,6 +25,12 @@ s = L.Sorter(n, r=args.r, variant=args.variant)
 for _ in range(args.reps):
     work.copy_(src)
     s.sort_(work)
+if args.pairs:
+    pk, pv = src.clone(), torch.arange(n, dtype=torch.int32, device="cuda")
+    L.PairSorter(n, r=args.r, variant=args.variant).sort_(pk, pv)
+    torch.cuda.synchronize()
+    assert bool((src[pv.long()] == pk).all()), "pairs: values do not follow their keys"
+    del pk, pv
 if args.scan:
     L.prefix_sum_(work, 256)
 torch.cuda.synchronize()

@@ -60,6 +60,17 @@ __device__ __forceinline__ uint32_t cell_offset(uint32_t key, uint32_t lane4)
     return (x & mask) | lane4;
 }
 
+// key store of the plain copy-out; CLR >= 2 selects a cache operator (tuning variants, see onesweep_r8.cu)
+template <int CLR>
+__device__ __forceinline__ void st_key(uint32_t* p, uint32_t v)
+{
+    if constexpr (CLR == 2) asm volatile("st.global.cg.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+    else if constexpr (CLR == 3) asm volatile("st.global.cs.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+    else if constexpr (CLR == 4) asm volatile("st.global.wt.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+    else if constexpr (CLR == 5) asm volatile("st.global.L1::no_allocate.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+    else *p = v;
+}
+
 template <int RB, int WARPS, int ITEMS, int MINB, int SHIFT, int LB, int CLR, int MODE, bool SP>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
 onesweep_lpc32_kernel(const PassArgs a)
@@ -487,12 +498,25 @@ onesweep_lpc32_kernel(const PassArgs a)
             const uint32_t d = (dpk[i >> 2] >> (8 * (i & 3))) & 0xFFu;
             if (p < valid) vout[s_gbase[d] + p] = s_keys[p];
         }
+    } else if (CLR == 6 && !typed_out) {
+        // tuning variant: one bucket run at a time per warp, lanes aligned to the 128-byte lines of the DESTINATION, so a
+        // run of L keys costs ceil((misalignment + L) / 32) line requests instead of the ~2.9 per 32 keys of the
+        // position-linear loop below (a warp there straddles two runs, each at its own alignment)
+        for (uint32_t d = warp; d < (uint32_t)H; d += WARPS) {
+            const uint32_t lo = s_dp[d];
+            uint32_t hi = d + 1 < (uint32_t)H ? s_dp[d + 1] : (uint32_t)TILE;
+            hi = hi < valid ? hi : valid;
+            const uint32_t gb = s_gbase[d];
+            const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(out + gb + lo) >> 2) & 31u;
+            for (uint32_t p = lo - mis + lane; (int32_t)(p - hi) < 0; p += 32)
+                if ((int32_t)(p - lo) >= 0) st_key<5>(out + gb + p, s_keys[p]);
+        }
     } else if (valid == (uint32_t)TILE && !typed_out) {
 #pragma unroll
         for (int i = 0; i < ITEMS; ++i) {
             const uint32_t p = i * THREADS + tid;
             const uint32_t k = s_keys[p];
-            out[s_gbase[(k >> SHIFT) & (H - 1)] + p] = k;
+            st_key<CLR>(out + s_gbase[(k >> SHIFT) & (H - 1)] + p, k);
         }
     } else {
         for (uint32_t p = tid; p < valid; p += THREADS) {

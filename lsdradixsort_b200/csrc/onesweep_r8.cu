@@ -10,7 +10,7 @@
 namespace lsd {
 
 static const OnesweepLauncher kTable[] = {
-    make_lpc32_launcher<8, 9, 29, 3, 4, 0, true>(),  // 0: default -- LPC ranking, 32-bit byte-offset counters, look-back window 4 (= variant 30)
+    make_lpc32_launcher<8, 9, 29, 3, 4, 5, true>(),  // 0: default -- LPC ranking, 32-bit byte-offset counters, look-back window 4, keys stored with L1::no_allocate (= variant 68)
     make_launcher<8, 128, 24, kMatchBallot>(),   // 1
     make_launcher<8, 256, 24, kMatchBallot, true>(),   // 2
     make_launcher<8, 1024, 8, kMatchBallot>(),   // 3
@@ -75,6 +75,11 @@ static const OnesweepLauncher kTable[] = {
     make_lpc2_launcher<8, 9, 29, 3, 8, 1, false, 1>(),   // 62: ... window 8
     make_lpc2_launcher<8, 9, 29, 3, 16, 1, false, 1>(),  // 63: ... window 16
     make_lpc2_launcher<8, 9, 29, 3, 8, 1>(),             // 64: two chains, strong polling, window 8
+    make_lpc32_launcher<8, 9, 29, 3, 4, 2>(),            // 65: as 0, keys stored with st.global.cg
+    make_lpc32_launcher<8, 9, 29, 3, 4, 3>(),            // 66: ... st.global.cs
+    make_lpc32_launcher<8, 9, 29, 3, 4, 4>(),            // 67: ... st.global.wt
+    make_lpc32_launcher<8, 9, 29, 3, 4, 5>(),            // 68: ... st.global.L1::no_allocate
+    make_lpc32_launcher<8, 9, 29, 3, 4, 6>(),            // 69: copy-out one bucket run per warp, lanes aligned to destination lines
 };
 
 const OnesweepLauncher* onesweep_table_r8(int* count)
