@@ -270,9 +270,15 @@ def run_ours(args):
     L.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     distributed = world > 1
+    stdout_fd = None
     if distributed:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # stdout carries exactly one JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        # stdout carries exactly ONE JSON line: NCCL writes its version banner to fd 1 whatever NCCL_DEBUG_FILE says, so
+        # fd 1 points at stderr until the line is printed
+        sys.stdout.flush()
+        stdout_fd = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev)
     total, name = workload(args)
     n_local = total // world
@@ -479,7 +485,10 @@ def run_ours(args):
         if stats is not None:
             line["exchange"] = dict(exchange or {}, sent_bytes_rank0=stats.sent_bytes, recv_bytes_rank0=stats.recv_bytes,
                                     keys_owned_rank0=stats.n_out)
-        print(json.dumps(line))
+        sys.stdout.flush()
+        if stdout_fd is not None:
+            os.dup2(stdout_fd, 1)
+        print(json.dumps(line), flush=True)
     if distributed:
         dist.destroy_process_group()
 

@@ -421,8 +421,20 @@ onesweep_lpc32_kernel(const PassArgs a)
         }
     }
     if (warp == 0) LSD_TRACE(7);  // warp 0 scattered
+    // key-value pass: the counter matrix (and the tile digit counts behind it) are dead after this barrier; the tile's
+    // VALUES are staged there by a second TMA copy that runs while the keys stream out.  Every thread orders its generic
+    // accesses to that region before the async-proxy write.
+    if constexpr (PAIRS) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
     if (warp == 0) LSD_TRACE(11);  // final barrier passed
+    static_assert(!PAIRS || S_::OFF_DP - S_::OFF_MAT >= TILE, "the value staging area (matrix + tile counts) must hold a tile");
+    if constexpr (PAIRS) {
+        if (valid == (uint32_t)TILE && tid == 0) {
+            const uint32_t* vsrc = (src_scratch ? a.vals_scratch : a.vals) + a.portion_base + tile_base;
+            mbar_expect_tx(s_bar, TILE * 4);
+            tma_bulk_g2s(s_mat, vsrc, TILE * 4, s_bar);
+        }
+    }
 
     // ---- 3. stream the reorder buffer out, coalesced per bucket ----
     // typed keys leave unsigned order when the last executed pass writes them (uniform over the grid)
@@ -456,33 +468,27 @@ onesweep_lpc32_kernel(const PassArgs a)
             if (p < valid) {
                 const uint32_t k = s_keys[p];
                 d = (k >> SHIFT) & (H - 1);
-                out[s_gbase[d] + p] = TYPED ? key_from_unsigned(k, xout) : k;
+                st_key<5>(out + s_gbase[d] + p, TYPED ? key_from_unsigned(k, xout) : k);
             }
             if (i & 3) dpk[i >> 2] |= d << (8 * (i & 3)); else dpk[i >> 2] = d;
         }
-        // every thread orders its generic accesses to the reorder buffer before the async-proxy write that follows
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncthreads();  // every key has left the reorder buffer: it becomes the staging buffer of the values
         const uint32_t* __restrict__ vin = (src_scratch ? a.vals_scratch : a.vals) + a.portion_base;
         uint32_t* __restrict__ vout = src_scratch ? a.vals : a.vals_scratch;
+        uint32_t* s_vals = s_mat;  // staging area of the values: the dead counter matrix (+ tile digit counts)
         if (valid == (uint32_t)TILE) {
-            if (tid == 0) {
-                mbar_expect_tx(s_bar, TILE * 4);
-                tma_bulk_g2s(s_keys, vin + tile_base, TILE * 4, s_bar);
-            }
-            mbar_wait(s_bar, 1);
+            mbar_wait(s_bar, 1);  // issued before the keys streamed out
         } else {
-            for (uint32_t p = tid; p < (uint32_t)TILE; p += THREADS) s_keys[p] = p < valid ? vin[tile_base + p] : 0u;
+            for (uint32_t p = tid; p < (uint32_t)TILE; p += THREADS) s_vals[p] = p < valid ? vin[tile_base + p] : 0u;
             __syncthreads();
         }
         // same lane-blocked ownership as the keys, same byte offsets (rk) in the reorder buffer
         uint32_t val[ITEMS];
         {
-            const uint32_t* src = s_keys + lane * S + warp * ITEMS;
+            const uint32_t* src = s_vals + lane * S + warp * ITEMS;
 #pragma unroll
             for (int i = 0; i < ITEMS; ++i) val[i] = src[i];
         }
-        __syncthreads();
+        __syncthreads();  // every key has left the reorder buffer: the values take the keys' places
         {
             char* kb = reinterpret_cast<char*>(s_keys);
 #pragma unroll
@@ -496,7 +502,7 @@ onesweep_lpc32_kernel(const PassArgs a)
         for (int i = 0; i < ITEMS; ++i) {
             const uint32_t p = i * THREADS + tid;
             const uint32_t d = (dpk[i >> 2] >> (8 * (i & 3))) & 0xFFu;
-            if (p < valid) vout[s_gbase[d] + p] = s_keys[p];
+            if (p < valid) st_key<5>(vout + s_gbase[d] + p, s_keys[p]);
         }
     } else if (CLR == 6 && !typed_out) {
         // tuning variant: one bucket run at a time per warp, lanes aligned to the 128-byte lines of the DESTINATION, so a
