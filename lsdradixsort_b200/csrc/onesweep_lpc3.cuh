@@ -1,0 +1,307 @@
+// onesweep_lpc3.cuh -- LPC32 pass as a PERSISTENT kernel that prefetches its next tile.
+//
+// In onesweep_lpc32_kernel a CTA lives for one tile: ticket, TMA load (~2 K cycles of DRAM latency under load), rank,
+// look-back, copy-out, exit.  The counter matrix is dead from the end of the rank chain on, while the reorder buffer is
+// still being streamed out.  Here a CTA loops over tickets and, right after the barrier that ends the ranking of tile k,
+// takes the ticket of tile k+1 and lets the TMA engine load it INTO THE DEAD MATRIX (+ tile-count area; together they
+// hold a tile) while tile k streams out.  Price: the matrix can only be cleared after the keys have been read out of it
+// (two more CTA-wide barriers per tile, and the clear no longer hides behind the load).
+// Plain key passes only; same tile, look-back protocol and workspace layout as onesweep_lpc32_kernel.
+#pragma once
+#include "onesweep_lpc32.cuh"
+
+namespace lsd {
+
+template <int RB, int WARPS, int ITEMS, int MINB, int SHIFT, int LB, int CLR>
+__global__ void __launch_bounds__(WARPS * 32, MINB)
+onesweep_lpc3_kernel(const PassArgs a)
+{
+    using S_ = Lpc32Shape<RB, WARPS, ITEMS>;
+    constexpr int H = S_::H, THREADS = S_::THREADS, S = S_::S, TILE = S_::TILE;
+    constexpr int SW = S_::SW, GPW = S_::GPW, LBT = S_::LBT, LBW = S_::LBW;
+    constexpr uint32_t kBarTot = 14, kBarScan = 15;
+    static_assert(S_::OFF_DP - S_::OFF_MAT >= TILE, "the prefetch area (matrix + tile counts) must hold a tile");
+    static_assert(LBT == H / 2, "one digit pair per look-back thread");
+
+    if (a.plan->skip[a.pass]) return;
+
+    extern __shared__ __align__(128) uint32_t smem[];
+    uint32_t* s_keys = smem;                     // reorder buffer
+    uint32_t* s_mat = smem + S_::OFF_MAT;        // counter matrix; between rank chain and next count: the incoming tile
+    uint32_t* s_in = s_mat;
+    uint32_t* s_tot = smem + S_::OFF_TOT;
+    uint32_t* s_dp = smem + S_::OFF_DP;
+    uint32_t* s_gbase = smem + S_::OFF_GBASE;
+    uint32_t* s_misc = smem + S_::OFF_MISC;
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_misc + 34);
+
+    const uint32_t tid = threadIdx.x;
+    const uint32_t lane = tid & 31u;
+    const uint32_t warp = tid >> 5;
+
+    const bool src_scratch = a.plan->src_is_scratch[a.pass] != 0;
+    const uint32_t* __restrict__ in = (src_scratch ? a.scratch : a.keys) + a.portion_base;
+    uint32_t* __restrict__ out = src_scratch ? a.keys : a.scratch;
+
+    // ticket of the next tile + its TMA load into s_in (thread 0 only)
+    auto fetch_next = [&]() {
+        const uint32_t t = atomicAdd(a.ticket, 1u);
+        s_misc[32] = t;
+        const uint32_t base = t * (uint32_t)TILE;
+        if (t < a.tiles && a.portion_keys - base >= (uint32_t)TILE) {
+            mbar_expect_tx(s_bar, TILE * 4);
+            tma_bulk_g2s(s_in, in + base, TILE * 4, s_bar);
+        }
+    };
+    if (tid == 0) {
+        mbar_init(s_bar, 1);
+        fetch_next();
+    }
+    __syncthreads();
+
+    char* mat_bytes = reinterpret_cast<char*>(s_mat);
+    const uint32_t lane4 = lane << 2;
+    uint32_t phase = 0;
+
+    while (true) {
+        const uint32_t tile = s_misc[32];
+        if (tile >= a.tiles) break;
+        const uint32_t tile_base = tile * (uint32_t)TILE;
+        const uint32_t left = a.portion_keys - tile_base;
+        const uint32_t valid = left < (uint32_t)TILE ? left : (uint32_t)TILE;
+        const uint32_t pads = (uint32_t)TILE - valid;
+
+        if (valid == (uint32_t)TILE) {
+            mbar_wait(s_bar, phase);
+            phase ^= 1u;
+        } else {
+            for (uint32_t p = tid; p < (uint32_t)TILE; p += THREADS) s_in[p] = p < valid ? in[tile_base + p] : 0xFFFFFFFFu;
+            __syncthreads();
+        }
+
+        // ---- 1. lane-blocked read, then the matrix takes its place back ----
+        uint32_t key[ITEMS];
+        {
+            const uint32_t* src = s_in + lane * S + warp * ITEMS;
+#pragma unroll
+            for (int i = 0; i < ITEMS; ++i) key[i] = src[i];
+        }
+        __syncthreads();  // every key is in registers
+        if constexpr (CLR == 1) {
+            // zero-fill by one st.bulk (UMEMSETS) instead of H*8 128-bit stores through the LSU
+            if (tid == 0) {
+                asm volatile("st.bulk.weak.shared::cta [%0], %1, 0;" ::"r"(smem_u32(s_mat)), "l"((uint64_t)(H * 128)) : "memory");
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            }
+        } else {
+            uint4* m4 = reinterpret_cast<uint4*>(s_mat);
+#pragma unroll
+            for (uint32_t i = tid; i < H * 8; i += THREADS) m4[i] = make_uint4(0, 0, 0, 0);
+        }
+        __syncthreads();  // matrix is zero
+#pragma unroll
+        for (int i = 0; i < ITEMS; ++i)
+            atomicAdd(reinterpret_cast<uint32_t*>(mat_bytes + cell_offset<RB, SHIFT>(key[i], lane4)), 4u);
+        __syncthreads();  // counts complete
+
+        uint32_t* lb_row = a.lookback + (size_t)tile * H;
+
+        if (warp < (uint32_t)SW) {
+            // ================= scan warps: totals -> bucket starts -> exclusive lane prefix =================
+            const uint32_t q = lane & 7u;
+            uint32_t total[GPW], below[GPW];
+#pragma unroll
+            for (int g = 0; g < GPW; ++g) {
+                const uint32_t row = (uint32_t)(g * SW + warp) * 32u + lane;
+                total[g] = 0;
+                below[g] = 0;
+                if (row < (uint32_t)H) {
+                    const uint4* r4 = reinterpret_cast<const uint4*>(s_mat + row * 32u);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const uint32_t grp = (q + k) & 7u;
+                        const uint4 v = r4[grp];
+                        const uint32_t s = v.x + v.y + v.z + v.w;
+                        total[g] += s;
+                        if (grp < q) below[g] += s;
+                    }
+                }
+            }
+            uint32_t start[GPW];
+            uint32_t carry = 0;
+#pragma unroll
+            for (int g = 0; g < GPW; ++g) {
+                uint32_t incl = total[g];
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t t = __shfl_up_sync(kFullMask, incl, o);
+                    if (lane >= (uint32_t)o) incl += t;
+                }
+                start[g] = incl - total[g];
+                if (lane == 31) s_misc[g * SW + warp] = incl;
+            }
+            if (SW > 1) named_bar_sync(kBarScan, SW * 32); else __syncwarp();
+#pragma unroll
+            for (int g = 0; g < GPW; ++g) {
+                uint32_t prefix = carry;
+#pragma unroll
+                for (int w = 0; w < SW; ++w) {
+                    const uint32_t part = s_misc[g * SW + w];
+                    if ((uint32_t)w < warp) prefix += part;
+                    carry += part;
+                }
+                start[g] += prefix;
+            }
+#pragma unroll
+            for (int g = 0; g < GPW; ++g) {
+                const uint32_t row = (uint32_t)(g * SW + warp) * 32u + lane;
+                if (row < (uint32_t)H) {
+                    s_tot[row] = total[g] >> 2;
+                    s_dp[row] = start[g] >> 2;
+                }
+            }
+            named_bar_arrive(kBarTot, (SW + LBW) * 32);
+#pragma unroll
+            for (int g = 0; g < GPW; ++g) {
+                const uint32_t row = (uint32_t)(g * SW + warp) * 32u + lane;
+                if (row < (uint32_t)H) {
+                    uint4* r4 = reinterpret_cast<uint4*>(s_mat + row * 32u);
+                    uint32_t run = start[g] + below[g];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const uint32_t grp = (q + k) & 7u;
+                        if (grp == 0) run = start[g];
+                        const uint4 v = r4[grp];
+                        uint4 o;
+                        o.x = run; run += v.x;
+                        o.y = run; run += v.y;
+                        o.z = run; run += v.z;
+                        o.w = run; run += v.w;
+                        r4[grp] = o;
+                    }
+                }
+            }
+            if (SW > 1) named_bar_sync(kBarScan, SW * 32);
+        } else if (warp >= (uint32_t)(WARPS - LBW)) {
+            // ================= look-back warps (tail of the rank chain): one digit pair per thread =================
+            named_bar_sync(kBarTot, (SW + LBW) * 32);
+            const uint32_t dt = tid - (uint32_t)(THREADS - LBT);
+            const uint32_t cnt_lo = s_tot[2 * dt];
+            uint32_t cnt_hi = s_tot[2 * dt + 1];
+            if (dt == (uint32_t)H / 2 - 1) cnt_hi -= pads;
+            const uint32_t dp_lo = s_dp[2 * dt], dp_hi = s_dp[2 * dt + 1];
+            uint32_t ex_lo = 0, ex_hi = 0;
+            if (tile == 0) {
+                st_relaxed_gpu_v2(lb_row + 2 * dt, kLbGlobal | cnt_lo, kLbGlobal | cnt_hi);
+            } else {
+                st_relaxed_gpu_v2(lb_row + 2 * dt, kLbLocal | cnt_lo, kLbLocal | cnt_hi);
+                const uint32_t* p = lb_row - H + 2 * dt;
+                uint32_t remaining = tile;
+                bool done = false;
+                while (!done) {
+                    uint2 w[LB];
+#pragma unroll
+                    for (int k = 0; k < LB; ++k)
+                        w[k] = (uint32_t)k < remaining ? ld_relaxed_gpu_v2(p - (size_t)k * H) : make_uint2(0u, 0u);
+                    uint32_t consumed = 0;
+#pragma unroll
+                    for (int k = 0; k < LB; ++k) {
+                        if (!done && consumed == (uint32_t)k && w[k].x != 0) {
+                            ex_lo += w[k].x & kLbValueMask;
+                            ex_hi += w[k].y & kLbValueMask;
+                            ++consumed;
+                            if (w[k].x & kLbGlobal) done = true;
+                        }
+                    }
+                    p -= (size_t)consumed * H;
+                    remaining -= consumed;
+                }
+                st_relaxed_gpu_v2(lb_row + 2 * dt, kLbGlobal | (ex_lo + cnt_lo), kLbGlobal | (ex_hi + cnt_hi));
+            }
+            const uint64_t b_lo = a.bases_in[2 * dt], b_hi = a.bases_in[2 * dt + 1];
+            s_gbase[2 * dt] = (uint32_t)b_lo + ex_lo - dp_lo;
+            s_gbase[2 * dt + 1] = (uint32_t)b_hi + ex_hi - dp_hi;
+            if (a.bases_out != nullptr && tile == a.tiles - 1) {
+                a.bases_out[2 * dt] = b_lo + ex_lo + cnt_lo;
+                a.bases_out[2 * dt + 1] = b_hi + ex_hi + cnt_hi;
+            }
+        }
+
+        // ---- 2. rank chain ----
+        uint32_t rk[(ITEMS + 1) / 2];
+        if (warp > 0) named_bar_sync(warp, 64);
+#pragma unroll
+        for (int i = 0; i < ITEMS; ++i) {
+            const uint32_t old = atomicAdd(reinterpret_cast<uint32_t*>(mat_bytes + cell_offset<RB, SHIFT>(key[i], lane4)), 4u);
+            if (i & 1) rk[i >> 1] = __byte_perm(rk[i >> 1], old, 0x5410); else rk[i >> 1] = old;
+        }
+        if (warp + 1 < (uint32_t)WARPS) named_bar_arrive(warp + 1, 64);
+        {
+            char* kb = reinterpret_cast<char*>(s_keys);
+#pragma unroll
+            for (int i = 0; i < ITEMS; ++i) {
+                const uint32_t off = (i & 1) ? (rk[i >> 1] >> 16) : (rk[i >> 1] & 0xFFFFu);
+                *reinterpret_cast<uint32_t*>(kb + off) = key[i];
+            }
+        }
+        // generic accesses to the matrix / tile counts are ordered before the async-proxy write of the next tile
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();  // reorder buffer complete; the matrix is dead
+
+        // ---- 3. next ticket + prefetch into the dead matrix, then stream this tile out ----
+        if (tid == 0) fetch_next();
+        if (valid == (uint32_t)TILE) {
+#pragma unroll
+            for (int i = 0; i < ITEMS; ++i) {
+                const uint32_t p = i * THREADS + tid;
+                const uint32_t k = s_keys[p];
+                st_key<5>(out + s_gbase[(k >> SHIFT) & (H - 1)] + p, k);
+            }
+        } else {
+            for (uint32_t p = tid; p < valid; p += THREADS) {
+                const uint32_t k = s_keys[p];
+                out[s_gbase[(k >> SHIFT) & (H - 1)] + p] = k;
+            }
+        }
+        __syncthreads();  // next ticket visible; reorder buffer and bucket bases free for the next tile
+    }
+}
+
+template <int RB, int WARPS, int ITEMS, int MINB, int SHIFT, int LB, int CLR>
+int onesweep_lpc3_launch_shift(const PassArgs& a, cudaStream_t s)
+{
+    using S_ = Lpc32Shape<RB, WARPS, ITEMS>;
+    auto kern = onesweep_lpc3_kernel<RB, WARPS, ITEMS, MINB, SHIFT, LB, CLR>;
+    LSD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S_::SMEM_BYTES));
+    LSD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    const uint32_t resident = (uint32_t)sm_count() * MINB;
+    const uint32_t grid = a.tiles < resident ? a.tiles : resident;  // persistent: every CTA loops over tickets
+    kern<<<grid, S_::THREADS, S_::SMEM_BYTES, s>>>(a);
+    LSD_LAUNCH_CHECK();
+    return LSD_OK;
+}
+
+template <int RB, int WARPS, int ITEMS, int MINB, int LB, int CLR>
+int onesweep_lpc3_launch(const PassArgs& a, cudaStream_t s)
+{
+    static_assert(RB == 8, "shift dispatch below is written for 8-bit digits");
+    switch (a.shift) {
+        case 0: return onesweep_lpc3_launch_shift<RB, WARPS, ITEMS, MINB, 0, LB, CLR>(a, s);
+        case 8: return onesweep_lpc3_launch_shift<RB, WARPS, ITEMS, MINB, 8, LB, CLR>(a, s);
+        case 16: return onesweep_lpc3_launch_shift<RB, WARPS, ITEMS, MINB, 16, LB, CLR>(a, s);
+        case 24: return onesweep_lpc3_launch_shift<RB, WARPS, ITEMS, MINB, 24, LB, CLR>(a, s);
+    }
+    return LSD_ERR_INVALID_VALUE;
+}
+
+constexpr int kModeLpc3 = 6;
+
+template <int RB, int WARPS, int ITEMS, int MINB, int LB, int CLR = 0>
+constexpr OnesweepLauncher make_lpc3_launcher()
+{
+    using S_ = Lpc32Shape<RB, WARPS, ITEMS>;
+    return OnesweepLauncher{RB, S_::THREADS, ITEMS, kModeLpc3, (uint32_t)S_::TILE, S_::PORTION_MAX, S_::SMEM_BYTES,
+                            &onesweep_lpc3_launch<RB, WARPS, ITEMS, MINB, LB, CLR>, nullptr, nullptr, nullptr, nullptr};
+}
+
+}  // namespace lsd

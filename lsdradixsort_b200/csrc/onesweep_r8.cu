@@ -3,6 +3,7 @@
 // reference's B) and lsd_sort_options.variant (tuning sweeps from bench_tools/).
 #include "onesweep_lpc32.cuh"
 #include "onesweep_lpc2.cuh"
+#include "onesweep_lpc3.cuh"
 #include "onesweep_lpcp.cuh"
 #include "onesweep_cpc.cuh"
 #include "onesweep_cpcp.cuh"
@@ -80,6 +81,11 @@ static const OnesweepLauncher kTable[] = {
     make_lpc32_launcher<8, 9, 29, 3, 4, 4>(),            // 67: ... st.global.wt
     make_lpc32_launcher<8, 9, 29, 3, 4, 5>(),            // 68: ... st.global.L1::no_allocate
     make_lpc32_launcher<8, 9, 29, 3, 4, 6>(),            // 69: copy-out one bucket run per warp, lanes aligned to destination lines
+    make_lpc3_launcher<8, 9, 29, 3, 4>(),                // 70: persistent LPC32, next tile prefetched into the dead counter matrix
+    make_lpc3_launcher<8, 9, 29, 3, 8>(),                // 71: ... look-back window 8
+    make_lpc3_launcher<8, 9, 29, 3, 4, 1>(),             // 72: ... matrix zero-filled by st.bulk
+    make_lpc3_launcher<8, 11, 23, 3, 4>(),               // 73: ... 352 threads, tile 8096
+    make_lpc3_launcher<8, 9, 29, 3, 2>(),                // 74: ... look-back window 2
 };
 
 const OnesweepLauncher* onesweep_table_r8(int* count)
