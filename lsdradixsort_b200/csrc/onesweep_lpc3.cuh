@@ -12,7 +12,17 @@
 
 namespace lsd {
 
-template <int RB, int WARPS, int ITEMS, int MINB, int SHIFT, int LB, int CLR>
+// 32 KiB of zeros in global memory: source of the TMA zero-fill of the counter matrix (CLR == 2)
+static __device__ __align__(128) uint4 g_lsd_zero_page[2048];
+
+__device__ __forceinline__ void mbar_arrive_release(uint64_t* bar)
+{
+    asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// CLR: 0 = matrix cleared with 128-bit stores, 1 = st.bulk, 2 = TMA copy of a zero page (keeps the clear off the LSU pipe)
+// NOB5: 1 = no CTA-wide barrier at the end of a tile: the next ticket is handed over through a second mbarrier
+template <int RB, int WARPS, int ITEMS, int MINB, int SHIFT, int LB, int CLR, int NOB5 = 0>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
 onesweep_lpc3_kernel(const PassArgs a)
 {
@@ -34,6 +44,7 @@ onesweep_lpc3_kernel(const PassArgs a)
     uint32_t* s_gbase = smem + S_::OFF_GBASE;
     uint32_t* s_misc = smem + S_::OFF_MISC;
     uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_misc + 34);
+    uint64_t* s_bar2 = reinterpret_cast<uint64_t*>(s_misc + 36);  // "next ticket is in s_misc[32]" (NOB5)
 
     const uint32_t tid = threadIdx.x;
     const uint32_t lane = tid & 31u;
@@ -55,15 +66,22 @@ onesweep_lpc3_kernel(const PassArgs a)
     };
     if (tid == 0) {
         mbar_init(s_bar, 1);
+        if constexpr (NOB5) mbar_init(s_bar2, 1);
         fetch_next();
+        if constexpr (NOB5) mbar_arrive_release(s_bar2);
     }
     __syncthreads();
+    uint32_t phase2 = 0;
 
     char* mat_bytes = reinterpret_cast<char*>(s_mat);
     const uint32_t lane4 = lane << 2;
     uint32_t phase = 0;
 
     while (true) {
+        if constexpr (NOB5) {
+            mbar_wait(s_bar2, phase2);
+            phase2 ^= 1u;
+        }
         const uint32_t tile = s_misc[32];
         if (tile >= a.tiles) break;
         const uint32_t tile_base = tile * (uint32_t)TILE;
@@ -86,8 +104,16 @@ onesweep_lpc3_kernel(const PassArgs a)
 #pragma unroll
             for (int i = 0; i < ITEMS; ++i) key[i] = src[i];
         }
+        if constexpr (CLR == 2) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // reads before the async zero-fill
         __syncthreads();  // every key is in registers
-        if constexpr (CLR == 1) {
+        if constexpr (CLR == 2) {
+            if (tid == 0) {
+                mbar_expect_tx(s_bar, H * 128);
+                tma_bulk_g2s(s_mat, g_lsd_zero_page, H * 128, s_bar);
+            }
+            mbar_wait(s_bar, phase);
+            phase ^= 1u;
+        } else if constexpr (CLR == 1) {
             // zero-fill by one st.bulk (UMEMSETS) instead of H*8 128-bit stores through the LSU
             if (tid == 0) {
                 asm volatile("st.bulk.weak.shared::cta [%0], %1, 0;" ::"r"(smem_u32(s_mat)), "l"((uint64_t)(H * 128)) : "memory");
@@ -98,7 +124,7 @@ onesweep_lpc3_kernel(const PassArgs a)
 #pragma unroll
             for (uint32_t i = tid; i < H * 8; i += THREADS) m4[i] = make_uint4(0, 0, 0, 0);
         }
-        __syncthreads();  // matrix is zero
+        if constexpr (CLR != 2) __syncthreads();  // matrix is zero
 #pragma unroll
         for (int i = 0; i < ITEMS; ++i)
             atomicAdd(reinterpret_cast<uint32_t*>(mat_bytes + cell_offset<RB, SHIFT>(key[i], lane4)), 4u);
@@ -249,7 +275,10 @@ onesweep_lpc3_kernel(const PassArgs a)
         __syncthreads();  // reorder buffer complete; the matrix is dead
 
         // ---- 3. next ticket + prefetch into the dead matrix, then stream this tile out ----
-        if (tid == 0) fetch_next();
+        if (tid == 0) {
+            fetch_next();
+            if constexpr (NOB5) mbar_arrive_release(s_bar2);
+        }
         if (valid == (uint32_t)TILE) {
 #pragma unroll
             for (int i = 0; i < ITEMS; ++i) {
@@ -263,15 +292,17 @@ onesweep_lpc3_kernel(const PassArgs a)
                 out[s_gbase[(k >> SHIFT) & (H - 1)] + p] = k;
             }
         }
-        __syncthreads();  // next ticket visible; reorder buffer and bucket bases free for the next tile
+        // next ticket visible; the reorder buffer and the bucket bases are not written again before the next tile's
+        // "every key is in registers" barrier, so with the mbarrier hand-over no barrier is needed here
+        if constexpr (!NOB5) __syncthreads();
     }
 }
 
-template <int RB, int WARPS, int ITEMS, int MINB, int SHIFT, int LB, int CLR>
+template <int RB, int WARPS, int ITEMS, int MINB, int SHIFT, int LB, int CLR, int NOB5>
 int onesweep_lpc3_launch_shift(const PassArgs& a, cudaStream_t s)
 {
     using S_ = Lpc32Shape<RB, WARPS, ITEMS>;
-    auto kern = onesweep_lpc3_kernel<RB, WARPS, ITEMS, MINB, SHIFT, LB, CLR>;
+    auto kern = onesweep_lpc3_kernel<RB, WARPS, ITEMS, MINB, SHIFT, LB, CLR, NOB5>;
     LSD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S_::SMEM_BYTES));
     LSD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     const uint32_t resident = (uint32_t)sm_count() * MINB;
@@ -281,27 +312,37 @@ int onesweep_lpc3_launch_shift(const PassArgs& a, cudaStream_t s)
     return LSD_OK;
 }
 
-template <int RB, int WARPS, int ITEMS, int MINB, int LB, int CLR>
+template <int RB, int WARPS, int ITEMS, int MINB, int LB, int CLR, int NOB5>
 int onesweep_lpc3_launch(const PassArgs& a, cudaStream_t s)
 {
     static_assert(RB == 8, "shift dispatch below is written for 8-bit digits");
     switch (a.shift) {
-        case 0: return onesweep_lpc3_launch_shift<RB, WARPS, ITEMS, MINB, 0, LB, CLR>(a, s);
-        case 8: return onesweep_lpc3_launch_shift<RB, WARPS, ITEMS, MINB, 8, LB, CLR>(a, s);
-        case 16: return onesweep_lpc3_launch_shift<RB, WARPS, ITEMS, MINB, 16, LB, CLR>(a, s);
-        case 24: return onesweep_lpc3_launch_shift<RB, WARPS, ITEMS, MINB, 24, LB, CLR>(a, s);
+        case 0: return onesweep_lpc3_launch_shift<RB, WARPS, ITEMS, MINB, 0, LB, CLR, NOB5>(a, s);
+        case 8: return onesweep_lpc3_launch_shift<RB, WARPS, ITEMS, MINB, 8, LB, CLR, NOB5>(a, s);
+        case 16: return onesweep_lpc3_launch_shift<RB, WARPS, ITEMS, MINB, 16, LB, CLR, NOB5>(a, s);
+        case 24: return onesweep_lpc3_launch_shift<RB, WARPS, ITEMS, MINB, 24, LB, CLR, NOB5>(a, s);
     }
     return LSD_ERR_INVALID_VALUE;
 }
 
 constexpr int kModeLpc3 = 6;
 
-template <int RB, int WARPS, int ITEMS, int MINB, int LB, int CLR = 0>
+// WITH_FORMS: the default entry -- plain passes on the persistent kernel, peer-scatter / key-value / typed-key passes on
+// onesweep_lpc32_kernel (same tile size, same workspace layout and look-back protocol).
+template <int RB, int WARPS, int ITEMS, int MINB, int LB, int CLR = 0, int NOB5 = 0, bool WITH_FORMS = false>
 constexpr OnesweepLauncher make_lpc3_launcher()
 {
     using S_ = Lpc32Shape<RB, WARPS, ITEMS>;
-    return OnesweepLauncher{RB, S_::THREADS, ITEMS, kModeLpc3, (uint32_t)S_::TILE, S_::PORTION_MAX, S_::SMEM_BYTES,
-                            &onesweep_lpc3_launch<RB, WARPS, ITEMS, MINB, LB, CLR>, nullptr, nullptr, nullptr, nullptr};
+    if constexpr (WITH_FORMS)
+        return OnesweepLauncher{RB, S_::THREADS, ITEMS, kModeLpc3, (uint32_t)S_::TILE, S_::PORTION_MAX, S_::SMEM_BYTES,
+                                &onesweep_lpc3_launch<RB, WARPS, ITEMS, MINB, LB, CLR, NOB5>,
+                                &onesweep_lpc32_launch<RB, WARPS, ITEMS, MINB, LB, 5, kPassPeer, false>,
+                                &onesweep_lpc32_launch<RB, WARPS, ITEMS, MINB, LB, 5, kPassPairs, false>,
+                                &onesweep_lpc32_launch<RB, WARPS, ITEMS, MINB, LB, 5, kPassTyped, false>,
+                                &onesweep_lpc32_launch<RB, WARPS, ITEMS, MINB, LB, 5, kPassPairsTyped, false>};
+    else
+        return OnesweepLauncher{RB, S_::THREADS, ITEMS, kModeLpc3, (uint32_t)S_::TILE, S_::PORTION_MAX, S_::SMEM_BYTES,
+                                &onesweep_lpc3_launch<RB, WARPS, ITEMS, MINB, LB, CLR, NOB5>, nullptr, nullptr, nullptr, nullptr};
 }
 
 }  // namespace lsd

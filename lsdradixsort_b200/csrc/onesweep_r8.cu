@@ -11,7 +11,7 @@
 namespace lsd {
 
 static const OnesweepLauncher kTable[] = {
-    make_lpc32_launcher<8, 9, 29, 3, 4, 5, true>(),  // 0: default -- LPC ranking, 32-bit byte-offset counters, look-back window 4, keys stored with L1::no_allocate (= variant 68)
+    make_lpc3_launcher<8, 9, 29, 3, 4, 0, 1, true>(),  // 0: default -- persistent LPC32 pass, next tile prefetched into the dead counter matrix, ticket hand-over by mbarrier (= variant 75); peer-scatter / key-value / typed-key passes on onesweep_lpc32_kernel (= variant 68)
     make_launcher<8, 128, 24, kMatchBallot>(),   // 1
     make_launcher<8, 256, 24, kMatchBallot, true>(),   // 2
     make_launcher<8, 1024, 8, kMatchBallot>(),   // 3
@@ -86,6 +86,9 @@ static const OnesweepLauncher kTable[] = {
     make_lpc3_launcher<8, 9, 29, 3, 4, 1>(),             // 72: ... matrix zero-filled by st.bulk
     make_lpc3_launcher<8, 11, 23, 3, 4>(),               // 73: ... 352 threads, tile 8096
     make_lpc3_launcher<8, 9, 29, 3, 2>(),                // 74: ... look-back window 2
+    make_lpc3_launcher<8, 9, 29, 3, 4, 0, 1>(),          // 75: as 70, ticket handed over through an mbarrier (no end-of-tile barrier)
+    make_lpc3_launcher<8, 9, 29, 3, 4, 2, 0>(),          // 76: as 70, matrix zero-filled by a TMA copy of a zero page
+    make_lpc3_launcher<8, 9, 29, 3, 4, 2, 1>(),          // 77: both
 };
 
 const OnesweepLauncher* onesweep_table_r8(int* count)
