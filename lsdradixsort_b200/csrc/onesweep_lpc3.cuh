@@ -22,7 +22,8 @@ __device__ __forceinline__ void mbar_arrive_release(uint64_t* bar)
 
 // CLR: 0 = matrix cleared with 128-bit stores, 1 = st.bulk, 2 = TMA copy of a zero page (keeps the clear off the LSU pipe)
 // NOB5: 1 = no CTA-wide barrier at the end of a tile: the next ticket is handed over through a second mbarrier
-template <int RB, int WARPS, int ITEMS, int MINB, int SHIFT, int LB, int CLR, int NOB5 = 0>
+// TYPED: i32 / f32 keys are mapped to unsigned order when the first executed pass reads them and back when the last one writes
+template <int RB, int WARPS, int ITEMS, int MINB, int SHIFT, int LB, int CLR, int NOB5 = 0, bool TYPED = false>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
 onesweep_lpc3_kernel(const PassArgs a)
 {
@@ -76,6 +77,9 @@ onesweep_lpc3_kernel(const PassArgs a)
     char* mat_bytes = reinterpret_cast<char*>(s_mat);
     const uint32_t lane4 = lane << 2;
     uint32_t phase = 0;
+    const KeyXform xin = TYPED ? pass_xform_in(a) : KeyXform{0u, 0u};
+    const bool typed_out = TYPED && a.plan->last_pass == (uint32_t)a.pass;
+    const KeyXform xout = key_xform_of(typed_out ? a.key_type : 0u);
 
     while (true) {
         if constexpr (NOB5) {
@@ -93,7 +97,8 @@ onesweep_lpc3_kernel(const PassArgs a)
             mbar_wait(s_bar, phase);
             phase ^= 1u;
         } else {
-            for (uint32_t p = tid; p < (uint32_t)TILE; p += THREADS) s_in[p] = p < valid ? in[tile_base + p] : 0xFFFFFFFFu;
+            const uint32_t pad_key = TYPED ? key_from_unsigned(0xFFFFFFFFu, xin) : 0xFFFFFFFFu;  // pads sort last
+            for (uint32_t p = tid; p < (uint32_t)TILE; p += THREADS) s_in[p] = p < valid ? in[tile_base + p] : pad_key;
             __syncthreads();
         }
 
@@ -102,7 +107,7 @@ onesweep_lpc3_kernel(const PassArgs a)
         {
             const uint32_t* src = s_in + lane * S + warp * ITEMS;
 #pragma unroll
-            for (int i = 0; i < ITEMS; ++i) key[i] = src[i];
+            for (int i = 0; i < ITEMS; ++i) key[i] = TYPED ? key_to_unsigned(src[i], xin) : src[i];
         }
         if constexpr (CLR == 2) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // reads before the async zero-fill
         __syncthreads();  // every key is in registers
@@ -279,7 +284,7 @@ onesweep_lpc3_kernel(const PassArgs a)
             fetch_next();
             if constexpr (NOB5) mbar_arrive_release(s_bar2);
         }
-        if (valid == (uint32_t)TILE) {
+        if (valid == (uint32_t)TILE && !typed_out) {
 #pragma unroll
             for (int i = 0; i < ITEMS; ++i) {
                 const uint32_t p = i * THREADS + tid;
@@ -289,7 +294,7 @@ onesweep_lpc3_kernel(const PassArgs a)
         } else {
             for (uint32_t p = tid; p < valid; p += THREADS) {
                 const uint32_t k = s_keys[p];
-                out[s_gbase[(k >> SHIFT) & (H - 1)] + p] = k;
+                out[s_gbase[(k >> SHIFT) & (H - 1)] + p] = TYPED ? key_from_unsigned(k, xout) : k;
             }
         }
         // next ticket visible; the reorder buffer and the bucket bases are not written again before the next tile's
@@ -298,11 +303,11 @@ onesweep_lpc3_kernel(const PassArgs a)
     }
 }
 
-template <int RB, int WARPS, int ITEMS, int MINB, int SHIFT, int LB, int CLR, int NOB5>
+template <int RB, int WARPS, int ITEMS, int MINB, int SHIFT, int LB, int CLR, int NOB5, bool TYPED>
 int onesweep_lpc3_launch_shift(const PassArgs& a, cudaStream_t s)
 {
     using S_ = Lpc32Shape<RB, WARPS, ITEMS>;
-    auto kern = onesweep_lpc3_kernel<RB, WARPS, ITEMS, MINB, SHIFT, LB, CLR, NOB5>;
+    auto kern = onesweep_lpc3_kernel<RB, WARPS, ITEMS, MINB, SHIFT, LB, CLR, NOB5, TYPED>;
     LSD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S_::SMEM_BYTES));
     LSD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     const uint32_t resident = (uint32_t)sm_count() * MINB;
@@ -312,22 +317,22 @@ int onesweep_lpc3_launch_shift(const PassArgs& a, cudaStream_t s)
     return LSD_OK;
 }
 
-template <int RB, int WARPS, int ITEMS, int MINB, int LB, int CLR, int NOB5>
+template <int RB, int WARPS, int ITEMS, int MINB, int LB, int CLR, int NOB5, bool TYPED = false>
 int onesweep_lpc3_launch(const PassArgs& a, cudaStream_t s)
 {
     static_assert(RB == 8, "shift dispatch below is written for 8-bit digits");
     switch (a.shift) {
-        case 0: return onesweep_lpc3_launch_shift<RB, WARPS, ITEMS, MINB, 0, LB, CLR, NOB5>(a, s);
-        case 8: return onesweep_lpc3_launch_shift<RB, WARPS, ITEMS, MINB, 8, LB, CLR, NOB5>(a, s);
-        case 16: return onesweep_lpc3_launch_shift<RB, WARPS, ITEMS, MINB, 16, LB, CLR, NOB5>(a, s);
-        case 24: return onesweep_lpc3_launch_shift<RB, WARPS, ITEMS, MINB, 24, LB, CLR, NOB5>(a, s);
+        case 0: return onesweep_lpc3_launch_shift<RB, WARPS, ITEMS, MINB, 0, LB, CLR, NOB5, TYPED>(a, s);
+        case 8: return onesweep_lpc3_launch_shift<RB, WARPS, ITEMS, MINB, 8, LB, CLR, NOB5, TYPED>(a, s);
+        case 16: return onesweep_lpc3_launch_shift<RB, WARPS, ITEMS, MINB, 16, LB, CLR, NOB5, TYPED>(a, s);
+        case 24: return onesweep_lpc3_launch_shift<RB, WARPS, ITEMS, MINB, 24, LB, CLR, NOB5, TYPED>(a, s);
     }
     return LSD_ERR_INVALID_VALUE;
 }
 
 constexpr int kModeLpc3 = 6;
 
-// WITH_FORMS: the default entry -- plain passes on the persistent kernel, peer-scatter / key-value / typed-key passes on
+// WITH_FORMS: the default entry -- plain and typed-key passes on the persistent kernel, peer-scatter and key-value passes on
 // onesweep_lpc32_kernel (same tile size, same workspace layout and look-back protocol).
 template <int RB, int WARPS, int ITEMS, int MINB, int LB, int CLR = 0, int NOB5 = 0, bool WITH_FORMS = false>
 constexpr OnesweepLauncher make_lpc3_launcher()
@@ -338,7 +343,7 @@ constexpr OnesweepLauncher make_lpc3_launcher()
                                 &onesweep_lpc3_launch<RB, WARPS, ITEMS, MINB, LB, CLR, NOB5>,
                                 &onesweep_lpc32_launch<RB, WARPS, ITEMS, MINB, LB, 5, kPassPeer, false>,
                                 &onesweep_lpc32_launch<RB, WARPS, ITEMS, MINB, LB, 5, kPassPairs, false>,
-                                &onesweep_lpc32_launch<RB, WARPS, ITEMS, MINB, LB, 5, kPassTyped, false>,
+                                &onesweep_lpc3_launch<RB, WARPS, ITEMS, MINB, LB, CLR, NOB5, true>,
                                 &onesweep_lpc32_launch<RB, WARPS, ITEMS, MINB, LB, 5, kPassPairsTyped, false>};
     else
         return OnesweepLauncher{RB, S_::THREADS, ITEMS, kModeLpc3, (uint32_t)S_::TILE, S_::PORTION_MAX, S_::SMEM_BYTES,
