@@ -23,7 +23,9 @@ __device__ __forceinline__ void mbar_arrive_release(uint64_t* bar)
 // CLR: 0 = matrix cleared with 128-bit stores, 1 = st.bulk, 2 = TMA copy of a zero page (keeps the clear off the LSU pipe)
 // NOB5: 1 = no CTA-wide barrier at the end of a tile: the next ticket is handed over through a second mbarrier
 // TYPED: i32 / f32 keys are mapped to unsigned order when the first executed pass reads them and back when the last one writes
-template <int RB, int WARPS, int ITEMS, int MINB, int SHIFT, int LB, int CLR, int NOB5 = 0, bool TYPED = false>
+// TRACE: per-tile phase clocks into PassArgs.trace (bench_tools/trace.py).  Compile-time: the run-time checks and the clock
+//        reads alone cost ~7 % of the pass (0.665 -> 0.715 ms), so only the tuning variant carries them.
+template <int RB, int WARPS, int ITEMS, int MINB, int SHIFT, int LB, int CLR, int NOB5 = 0, bool TYPED = false, bool TRACE = false>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
 onesweep_lpc3_kernel(const PassArgs a)
 {
@@ -88,6 +90,12 @@ onesweep_lpc3_kernel(const PassArgs a)
         }
         const uint32_t tile = s_misc[32];
         if (tile >= a.tiles) break;
+        const long long t_start = (TRACE && a.trace) ? clock64() : 0;  // phase clocks count from the moment the ticket is known
+#define LSD_TRACE(slot)                                                                      \
+    do {                                                                                     \
+        if constexpr (TRACE)                                                                 \
+            if (a.trace && lane == 0) a.trace[(size_t)tile * 16 + (slot)] = (unsigned long long)(clock64() - t_start); \
+    } while (0)
         const uint32_t tile_base = tile * (uint32_t)TILE;
         const uint32_t left = a.portion_keys - tile_base;
         const uint32_t valid = left < (uint32_t)TILE ? left : (uint32_t)TILE;
@@ -102,6 +110,7 @@ onesweep_lpc3_kernel(const PassArgs a)
             __syncthreads();
         }
 
+        if (warp == 0) LSD_TRACE(1);  // tile landed
         // ---- 1. lane-blocked read, then the matrix takes its place back ----
         uint32_t key[ITEMS];
         {
@@ -130,10 +139,13 @@ onesweep_lpc3_kernel(const PassArgs a)
             for (uint32_t i = tid; i < H * 8; i += THREADS) m4[i] = make_uint4(0, 0, 0, 0);
         }
         if constexpr (CLR != 2) __syncthreads();  // matrix is zero
+        if (warp == 0) LSD_TRACE(0);  // keys read, matrix cleared
 #pragma unroll
         for (int i = 0; i < ITEMS; ++i)
             atomicAdd(reinterpret_cast<uint32_t*>(mat_bytes + cell_offset<RB, SHIFT>(key[i], lane4)), 4u);
+        if (warp == 0) LSD_TRACE(2);
         __syncthreads();  // counts complete
+        if (warp == 0) LSD_TRACE(3);
 
         uint32_t* lb_row = a.lookback + (size_t)tile * H;
 
@@ -192,6 +204,7 @@ onesweep_lpc3_kernel(const PassArgs a)
                 }
             }
             named_bar_arrive(kBarTot, (SW + LBW) * 32);
+            if (warp == 0) LSD_TRACE(4);
 #pragma unroll
             for (int g = 0; g < GPW; ++g) {
                 const uint32_t row = (uint32_t)(g * SW + warp) * 32u + lane;
@@ -213,9 +226,11 @@ onesweep_lpc3_kernel(const PassArgs a)
                 }
             }
             if (SW > 1) named_bar_sync(kBarScan, SW * 32);
+            if (warp == 0) LSD_TRACE(5);
         } else if (warp >= (uint32_t)(WARPS - LBW)) {
             // ================= look-back warps (tail of the rank chain): one digit pair per thread =================
             named_bar_sync(kBarTot, (SW + LBW) * 32);
+            if (warp == (uint32_t)WARPS - 1) LSD_TRACE(8);
             const uint32_t dt = tid - (uint32_t)(THREADS - LBT);
             const uint32_t cnt_lo = s_tot[2 * dt];
             uint32_t cnt_hi = s_tot[2 * dt + 1];
@@ -229,7 +244,9 @@ onesweep_lpc3_kernel(const PassArgs a)
                 const uint32_t* p = lb_row - H + 2 * dt;
                 uint32_t remaining = tile;
                 bool done = false;
+                [[maybe_unused]] uint32_t dbg_rounds = 0, dbg_hops = 0;
                 while (!done) {
+                    if constexpr (TRACE) ++dbg_rounds;
                     uint2 w[LB];
 #pragma unroll
                     for (int k = 0; k < LB; ++k)
@@ -246,7 +263,13 @@ onesweep_lpc3_kernel(const PassArgs a)
                     }
                     p -= (size_t)consumed * H;
                     remaining -= consumed;
+                    if constexpr (TRACE) dbg_hops += consumed;
                 }
+                if constexpr (TRACE)
+                    if (a.trace && warp == (uint32_t)WARPS - 1 && lane == 0) {
+                        a.trace[(size_t)tile * 16 + 13] = dbg_rounds;
+                        a.trace[(size_t)tile * 16 + 14] = dbg_hops;
+                    }
                 st_relaxed_gpu_v2(lb_row + 2 * dt, kLbGlobal | (ex_lo + cnt_lo), kLbGlobal | (ex_hi + cnt_hi));
             }
             const uint64_t b_lo = a.bases_in[2 * dt], b_hi = a.bases_in[2 * dt + 1];
@@ -258,6 +281,7 @@ onesweep_lpc3_kernel(const PassArgs a)
             }
         }
 
+        if (warp == (uint32_t)WARPS - 1) LSD_TRACE(9);  // look-back done (last warp)
         // ---- 2. rank chain ----
         uint32_t rk[(ITEMS + 1) / 2];
         if (warp > 0) named_bar_sync(warp, 64);
@@ -267,6 +291,8 @@ onesweep_lpc3_kernel(const PassArgs a)
             if (i & 1) rk[i >> 1] = __byte_perm(rk[i >> 1], old, 0x5410); else rk[i >> 1] = old;
         }
         if (warp + 1 < (uint32_t)WARPS) named_bar_arrive(warp + 1, 64);
+        if (warp == 0) LSD_TRACE(6);
+        if (warp == (uint32_t)WARPS - 1) LSD_TRACE(10);
         {
             char* kb = reinterpret_cast<char*>(s_keys);
 #pragma unroll
@@ -278,6 +304,7 @@ onesweep_lpc3_kernel(const PassArgs a)
         // generic accesses to the matrix / tile counts are ordered before the async-proxy write of the next tile
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();  // reorder buffer complete; the matrix is dead
+        if (warp == 0) LSD_TRACE(11);
 
         // ---- 3. next ticket + prefetch into the dead matrix, then stream this tile out ----
         if (tid == 0) {
@@ -297,17 +324,19 @@ onesweep_lpc3_kernel(const PassArgs a)
                 out[s_gbase[(k >> SHIFT) & (H - 1)] + p] = TYPED ? key_from_unsigned(k, xout) : k;
             }
         }
+        if (warp == 0) LSD_TRACE(12);
+#undef LSD_TRACE
         // next ticket visible; the reorder buffer and the bucket bases are not written again before the next tile's
         // "every key is in registers" barrier, so with the mbarrier hand-over no barrier is needed here
         if constexpr (!NOB5) __syncthreads();
     }
 }
 
-template <int RB, int WARPS, int ITEMS, int MINB, int SHIFT, int LB, int CLR, int NOB5, bool TYPED>
+template <int RB, int WARPS, int ITEMS, int MINB, int SHIFT, int LB, int CLR, int NOB5, bool TYPED, bool TRACE>
 int onesweep_lpc3_launch_shift(const PassArgs& a, cudaStream_t s)
 {
     using S_ = Lpc32Shape<RB, WARPS, ITEMS>;
-    auto kern = onesweep_lpc3_kernel<RB, WARPS, ITEMS, MINB, SHIFT, LB, CLR, NOB5, TYPED>;
+    auto kern = onesweep_lpc3_kernel<RB, WARPS, ITEMS, MINB, SHIFT, LB, CLR, NOB5, TYPED, TRACE>;
     LSD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S_::SMEM_BYTES));
     LSD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     const uint32_t resident = (uint32_t)sm_count() * MINB;
@@ -317,15 +346,15 @@ int onesweep_lpc3_launch_shift(const PassArgs& a, cudaStream_t s)
     return LSD_OK;
 }
 
-template <int RB, int WARPS, int ITEMS, int MINB, int LB, int CLR, int NOB5, bool TYPED = false>
+template <int RB, int WARPS, int ITEMS, int MINB, int LB, int CLR, int NOB5, bool TYPED = false, bool TRACE = false>
 int onesweep_lpc3_launch(const PassArgs& a, cudaStream_t s)
 {
     static_assert(RB == 8, "shift dispatch below is written for 8-bit digits");
     switch (a.shift) {
-        case 0: return onesweep_lpc3_launch_shift<RB, WARPS, ITEMS, MINB, 0, LB, CLR, NOB5, TYPED>(a, s);
-        case 8: return onesweep_lpc3_launch_shift<RB, WARPS, ITEMS, MINB, 8, LB, CLR, NOB5, TYPED>(a, s);
-        case 16: return onesweep_lpc3_launch_shift<RB, WARPS, ITEMS, MINB, 16, LB, CLR, NOB5, TYPED>(a, s);
-        case 24: return onesweep_lpc3_launch_shift<RB, WARPS, ITEMS, MINB, 24, LB, CLR, NOB5, TYPED>(a, s);
+        case 0: return onesweep_lpc3_launch_shift<RB, WARPS, ITEMS, MINB, 0, LB, CLR, NOB5, TYPED, TRACE>(a, s);
+        case 8: return onesweep_lpc3_launch_shift<RB, WARPS, ITEMS, MINB, 8, LB, CLR, NOB5, TYPED, TRACE>(a, s);
+        case 16: return onesweep_lpc3_launch_shift<RB, WARPS, ITEMS, MINB, 16, LB, CLR, NOB5, TYPED, TRACE>(a, s);
+        case 24: return onesweep_lpc3_launch_shift<RB, WARPS, ITEMS, MINB, 24, LB, CLR, NOB5, TYPED, TRACE>(a, s);
     }
     return LSD_ERR_INVALID_VALUE;
 }
@@ -334,7 +363,7 @@ constexpr int kModeLpc3 = 6;
 
 // WITH_FORMS: the default entry -- plain and typed-key passes on the persistent kernel, peer-scatter and key-value passes on
 // onesweep_lpc32_kernel (same tile size, same workspace layout and look-back protocol).
-template <int RB, int WARPS, int ITEMS, int MINB, int LB, int CLR = 0, int NOB5 = 0, bool WITH_FORMS = false>
+template <int RB, int WARPS, int ITEMS, int MINB, int LB, int CLR = 0, int NOB5 = 0, bool WITH_FORMS = false, bool TRACE = false>
 constexpr OnesweepLauncher make_lpc3_launcher()
 {
     using S_ = Lpc32Shape<RB, WARPS, ITEMS>;
@@ -347,7 +376,8 @@ constexpr OnesweepLauncher make_lpc3_launcher()
                                 &onesweep_lpc32_launch<RB, WARPS, ITEMS, MINB, LB, 5, kPassPairsTyped, false>};
     else
         return OnesweepLauncher{RB, S_::THREADS, ITEMS, kModeLpc3, (uint32_t)S_::TILE, S_::PORTION_MAX, S_::SMEM_BYTES,
-                                &onesweep_lpc3_launch<RB, WARPS, ITEMS, MINB, LB, CLR, NOB5>, nullptr, nullptr, nullptr, nullptr};
+                                &onesweep_lpc3_launch<RB, WARPS, ITEMS, MINB, LB, CLR, NOB5, false, TRACE>, nullptr, nullptr, nullptr,
+                                nullptr};
 }
 
 }  // namespace lsd

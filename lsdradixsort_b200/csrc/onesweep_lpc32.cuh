@@ -102,10 +102,14 @@ onesweep_lpc32_kernel(const PassArgs a)
     const uint32_t* __restrict__ in = (src_scratch ? a.scratch : a.keys) + a.portion_base;
     uint32_t* __restrict__ out = src_scratch ? a.keys : a.scratch;
 
-    const long long t_start = a.trace ? clock64() : 0;
+    // the per-tile phase trace (bench_tools/trace.py) is compiled into the plain CLR == 0 tuning variants only: its run-time
+    // checks and clock reads alone cost several per cent of a pass
+    constexpr bool TRACE = CLR == 0 && MODE == kPassPlain;
+    const long long t_start = (TRACE && a.trace) ? clock64() : 0;
 #define LSD_TRACE(slot)                                                                      \
     do {                                                                                     \
-        if (a.trace && lane == 0) a.trace[(size_t)tile * 16 + (slot)] = (unsigned long long)(clock64() - t_start); \
+        if constexpr (TRACE)                                                                 \
+            if (a.trace && lane == 0) a.trace[(size_t)tile * 16 + (slot)] = (unsigned long long)(clock64() - t_start); \
     } while (0)
 
     // ---- 0. ticket, TMA bulk load, clear the matrix ----
@@ -379,10 +383,11 @@ onesweep_lpc32_kernel(const PassArgs a)
                     remaining -= consumed;
                     dbg_hops += consumed;
                 }
-                if (a.trace && warp == (uint32_t)WARPS - 1 && lane == 0) {
-                    a.trace[(size_t)tile * 16 + 13] = dbg_rounds;
-                    a.trace[(size_t)tile * 16 + 14] = dbg_hops;
-                }
+                if constexpr (TRACE)
+                    if (a.trace && warp == (uint32_t)WARPS - 1 && lane == 0) {
+                        a.trace[(size_t)tile * 16 + 13] = dbg_rounds;
+                        a.trace[(size_t)tile * 16 + 14] = dbg_hops;
+                    }
                 st_relaxed_gpu_v2(lb_row + 2 * dt, kLbGlobal | (ex_lo + cnt_lo), kLbGlobal | (ex_hi + cnt_hi));
             }
             const uint64_t b_lo = a.bases_in[2 * dt], b_hi = a.bases_in[2 * dt + 1];
