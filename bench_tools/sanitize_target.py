@@ -22,6 +22,12 @@ for n in (50_001, 200_000):
             w = d.clone()
             L.sort_(w, r=r)
             assert np.array_equal(w.cpu().numpy().view(np.uint32), np.sort(keys))
+        kv, vv = d.clone(), torch.arange(n, dtype=torch.int32, device="cuda")
+        L.sort_pairs_(kv, vv, r=8)                      # key-value pass (values staged in the dead matrix)
+        assert np.array_equal(vv.cpu().numpy().view(np.uint32), np.argsort(keys, kind="stable").astype(np.uint32))
+        f = torch.from_numpy(keys.view(np.float32)).cuda()
+        L.sort_(f)                                      # typed flavour of the persistent kernel (f32 total order)
+        L.sort_(d.clone(), r=8, key_type="i32")
         s = d.clone()
         L.prefix_sum_(s, 256)
         L.digit_histograms(d, 8)

@@ -439,3 +439,64 @@ def test_sort_is_cuda_graph_capturable():
         g.replay()
         torch.cuda.synchronize()
         assert np.array_equal(host(buf), _oracle.sort(keys, 8)), kind
+
+
+def test_sort_writes_nothing_outside_its_buffers():
+    """compute-sanitizer is closed on the GPU pool, so the bounds check is done by hand: keys, scratch and workspace are
+    carved out of one allocation with guard zones in between; the guards must survive plain, typed and key-value sorts."""
+    guard = 4096  # int32 words, 16 KiB
+    for n in (1, 8351, 8352, 8353, 100_003, 444 * 8352 + 17):
+        ws_words = (max(L.sort_workspace_bytes(n, 8, 0), 256) + 3) // 4
+        ws_words = (ws_words + 63) // 64 * 64
+        n_pad = (n + 63) // 64 * 64
+        sizes = [n_pad, n_pad, n_pad, n_pad, ws_words]  # keys, scratch, vals, vals_scratch, workspace
+        total = sum(sizes) + guard * (len(sizes) + 1)
+        arena = torch.full((total,), 0x5A5A5A5A, dtype=torch.int32, device="cuda")
+        offs, o = [], guard
+        for s in sizes:
+            offs.append(o)
+            o += s + guard
+        keys_np = keygen.make_keys("uniform", n, seed=n)
+        views = [arena[a:a + s] for a, s in zip(offs, sizes)]
+        k, sc, v, vs, ws = views
+        for flavour in ("plain", "f32", "pairs"):
+            k[:n] = dev(keys_np)
+            ws_bytes = ws.view(torch.uint8)
+            if flavour == "pairs":
+                v[:n] = torch.arange(n, dtype=torch.int32, device="cuda")
+                st = N.lib().lsd_sort_pairs(k.data_ptr(), v.data_ptr(), sc.data_ptr(), vs.data_ptr(), n, 8, 0, ws.data_ptr(),
+                                            ws_bytes.numel(), None, torch.cuda.current_stream().cuda_stream)
+            else:
+                o = N.SortOptions(C.sizeof(N.SortOptions), 0, 0, 0, 0, N.LSD_KEY_F32 if flavour == "f32" else 0, 0)
+                st = N.lib().lsd_sort_ex(k.data_ptr(), sc.data_ptr(), n, 8, 0, ws.data_ptr(), ws_bytes.numel(), C.byref(o),
+                                         torch.cuda.current_stream().cuda_stream)
+            assert st == 0
+            torch.cuda.synchronize()
+            want = _oracle.sort_typed(keys_np, "f32", 8) if flavour == "f32" else _oracle.sort(keys_np, 8)
+            assert np.array_equal(host(k[:n]), want), (n, flavour)
+            prev_end = 0
+            for a, s in zip(offs + [total], sizes + [0]):
+                g = arena[prev_end:a]
+                assert bool((g == 0x5A5A5A5A).all()), f"guard before offset {a} was overwritten (n={n}, {flavour})"
+                prev_end = a + s
+            for t, s in zip((k, sc), (n, n)):  # padding words behind the n keys of keys / scratch stay untouched too
+                assert bool((t[s:] == 0x5A5A5A5A).all()), (n, flavour)
+
+
+def test_sort_stress_random_sizes_against_torch():
+    """Many back-to-back sorts of random sizes and distributions on one Sorter (persistent kernel, ticket hand-over through
+    an mbarrier, look-back across tiles): any rare ordering bug shows up as a mismatch with torch.sort."""
+    g = torch.Generator(device="cuda").manual_seed(7)
+    rng = np.random.default_rng(7)
+    cap = 3_000_000
+    s = L.Sorter(cap, r=8)
+    for it in range(150):
+        n = int(rng.integers(1, cap))
+        bits = int(rng.choice([4, 12, 20, 32]))
+        hi = (1 << bits) - 1
+        k = torch.randint(0, hi + 1, (n,), dtype=torch.int64, device="cuda", generator=g)
+        want, _ = torch.sort(k)
+        work = (k & 0xFFFFFFFF).to(torch.int32) if bits < 32 else (k - (k >> 31 << 32)).to(torch.int32)
+        s.sort_(work)
+        got = work.to(torch.int64) & 0xFFFFFFFF
+        assert bool((got == want).all()), (it, n, bits)
