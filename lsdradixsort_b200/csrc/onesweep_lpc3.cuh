@@ -6,7 +6,10 @@
 // takes the ticket of tile k+1 and lets the TMA engine load it INTO THE DEAD MATRIX (+ tile-count area; together they
 // hold a tile) while tile k streams out.  Price: the matrix can only be cleared after the keys have been read out of it
 // (two more CTA-wide barriers per tile, and the clear no longer hides behind the load).
-// Plain key passes only; same tile, look-back protocol and workspace layout as onesweep_lpc32_kernel.
+// Plain and typed-key passes; same tile, look-back protocol and workspace layout as onesweep_lpc32_kernel.
+// Digits narrower than 8 bits (r = 1, 2, 4: the reference's other radix settings) have a counter matrix far smaller than a
+// tile, so there the prefetch goes to a dedicated second tile buffer (the shared-memory budget per CTA is the same) and the
+// digit shift is a run-time value (SHIFT < 0) to keep the number of instantiations down.
 #pragma once
 #include "onesweep_lpc32.cuh"
 
@@ -33,15 +36,17 @@ onesweep_lpc3_kernel(const PassArgs a)
     constexpr int H = S_::H, THREADS = S_::THREADS, S = S_::S, TILE = S_::TILE;
     constexpr int SW = S_::SW, GPW = S_::GPW, LBT = S_::LBT, LBW = S_::LBW;
     constexpr uint32_t kBarTot = 14, kBarScan = 15;
-    static_assert(S_::OFF_DP - S_::OFF_MAT >= TILE, "the prefetch area (matrix + tile counts) must hold a tile");
-    static_assert(LBT == H / 2, "one digit pair per look-back thread");
+    constexpr bool ALIAS = S_::OFF_DP - S_::OFF_MAT >= TILE;  // the dead matrix (+ tile counts) can hold the incoming tile
+    constexpr int IN_OFF = (S_::WORDS + 3) & ~3;               // else: a dedicated prefetch buffer behind everything
+    static_assert(LBT >= H / 2, "one digit pair per look-back thread");
+    const int shift = SHIFT >= 0 ? SHIFT : a.shift;
 
     if (a.plan->skip[a.pass]) return;
 
     extern __shared__ __align__(128) uint32_t smem[];
     uint32_t* s_keys = smem;                     // reorder buffer
     uint32_t* s_mat = smem + S_::OFF_MAT;        // counter matrix; between rank chain and next count: the incoming tile
-    uint32_t* s_in = s_mat;
+    uint32_t* s_in = ALIAS ? s_mat : smem + IN_OFF;
     uint32_t* s_tot = smem + S_::OFF_TOT;
     uint32_t* s_dp = smem + S_::OFF_DP;
     uint32_t* s_gbase = smem + S_::OFF_GBASE;
@@ -78,6 +83,10 @@ onesweep_lpc3_kernel(const PassArgs a)
 
     char* mat_bytes = reinterpret_cast<char*>(s_mat);
     const uint32_t lane4 = lane << 2;
+    auto cell_of = [&](uint32_t key) -> uint32_t {  // byte offset of cell (digit, lane) in the matrix
+        if constexpr (SHIFT >= 0) return cell_offset<RB, SHIFT < 0 ? 0 : SHIFT>(key, lane4);
+        else return (((key >> shift) & (uint32_t)(H - 1)) << 7) | lane4;
+    };
     uint32_t phase = 0;
     const KeyXform xin = TYPED ? pass_xform_in(a) : KeyXform{0u, 0u};
     const bool typed_out = TYPED && a.plan->last_pass == (uint32_t)a.pass;
@@ -142,7 +151,7 @@ onesweep_lpc3_kernel(const PassArgs a)
         if (warp == 0) LSD_TRACE(0);  // keys read, matrix cleared
 #pragma unroll
         for (int i = 0; i < ITEMS; ++i)
-            atomicAdd(reinterpret_cast<uint32_t*>(mat_bytes + cell_offset<RB, SHIFT>(key[i], lane4)), 4u);
+            atomicAdd(reinterpret_cast<uint32_t*>(mat_bytes + cell_of(key[i])), 4u);
         if (warp == 0) LSD_TRACE(2);
         __syncthreads();  // counts complete
         if (warp == 0) LSD_TRACE(3);
@@ -232,6 +241,7 @@ onesweep_lpc3_kernel(const PassArgs a)
             named_bar_sync(kBarTot, (SW + LBW) * 32);
             if (warp == (uint32_t)WARPS - 1) LSD_TRACE(8);
             const uint32_t dt = tid - (uint32_t)(THREADS - LBT);
+            if (dt < (uint32_t)H / 2) {
             const uint32_t cnt_lo = s_tot[2 * dt];
             uint32_t cnt_hi = s_tot[2 * dt + 1];
             if (dt == (uint32_t)H / 2 - 1) cnt_hi -= pads;
@@ -279,6 +289,7 @@ onesweep_lpc3_kernel(const PassArgs a)
                 a.bases_out[2 * dt] = b_lo + ex_lo + cnt_lo;
                 a.bases_out[2 * dt + 1] = b_hi + ex_hi + cnt_hi;
             }
+            }
         }
 
         if (warp == (uint32_t)WARPS - 1) LSD_TRACE(9);  // look-back done (last warp)
@@ -287,7 +298,7 @@ onesweep_lpc3_kernel(const PassArgs a)
         if (warp > 0) named_bar_sync(warp, 64);
 #pragma unroll
         for (int i = 0; i < ITEMS; ++i) {
-            const uint32_t old = atomicAdd(reinterpret_cast<uint32_t*>(mat_bytes + cell_offset<RB, SHIFT>(key[i], lane4)), 4u);
+            const uint32_t old = atomicAdd(reinterpret_cast<uint32_t*>(mat_bytes + cell_of(key[i])), 4u);
             if (i & 1) rk[i >> 1] = __byte_perm(rk[i >> 1], old, 0x5410); else rk[i >> 1] = old;
         }
         if (warp + 1 < (uint32_t)WARPS) named_bar_arrive(warp + 1, 64);
@@ -316,12 +327,12 @@ onesweep_lpc3_kernel(const PassArgs a)
             for (int i = 0; i < ITEMS; ++i) {
                 const uint32_t p = i * THREADS + tid;
                 const uint32_t k = s_keys[p];
-                st_key<5>(out + s_gbase[(k >> SHIFT) & (H - 1)] + p, k);
+                st_key<5>(out + s_gbase[(k >> shift) & (H - 1)] + p, k);
             }
         } else {
             for (uint32_t p = tid; p < valid; p += THREADS) {
                 const uint32_t k = s_keys[p];
-                out[s_gbase[(k >> SHIFT) & (H - 1)] + p] = TYPED ? key_from_unsigned(k, xout) : k;
+                out[s_gbase[(k >> shift) & (H - 1)] + p] = TYPED ? key_from_unsigned(k, xout) : k;
             }
         }
         if (warp == 0) LSD_TRACE(12);
@@ -337,11 +348,13 @@ int onesweep_lpc3_launch_shift(const PassArgs& a, cudaStream_t s)
 {
     using S_ = Lpc32Shape<RB, WARPS, ITEMS>;
     auto kern = onesweep_lpc3_kernel<RB, WARPS, ITEMS, MINB, SHIFT, LB, CLR, NOB5, TYPED, TRACE>;
-    LSD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S_::SMEM_BYTES));
+    constexpr bool ALIAS = S_::OFF_DP - S_::OFF_MAT >= S_::TILE;
+    constexpr size_t SMEM = ALIAS ? S_::SMEM_BYTES : sizeof(uint32_t) * (((S_::WORDS + 3) & ~3) + S_::TILE) + 16;
+    LSD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
     LSD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     const uint32_t resident = (uint32_t)sm_count() * MINB;
     const uint32_t grid = a.tiles < resident ? a.tiles : resident;  // persistent: every CTA loops over tickets
-    kern<<<grid, S_::THREADS, S_::SMEM_BYTES, s>>>(a);
+    kern<<<grid, S_::THREADS, SMEM, s>>>(a);
     LSD_LAUNCH_CHECK();
     return LSD_OK;
 }
@@ -349,7 +362,7 @@ int onesweep_lpc3_launch_shift(const PassArgs& a, cudaStream_t s)
 template <int RB, int WARPS, int ITEMS, int MINB, int LB, int CLR, int NOB5, bool TYPED = false, bool TRACE = false>
 int onesweep_lpc3_launch(const PassArgs& a, cudaStream_t s)
 {
-    static_assert(RB == 8, "shift dispatch below is written for 8-bit digits");
+    if constexpr (RB != 8) return onesweep_lpc3_launch_shift<RB, WARPS, ITEMS, MINB, -1, LB, CLR, NOB5, TYPED, TRACE>(a, s);
     switch (a.shift) {
         case 0: return onesweep_lpc3_launch_shift<RB, WARPS, ITEMS, MINB, 0, LB, CLR, NOB5, TYPED, TRACE>(a, s);
         case 8: return onesweep_lpc3_launch_shift<RB, WARPS, ITEMS, MINB, 8, LB, CLR, NOB5, TYPED, TRACE>(a, s);
@@ -361,19 +374,24 @@ int onesweep_lpc3_launch(const PassArgs& a, cudaStream_t s)
 
 constexpr int kModeLpc3 = 6;
 
-// WITH_FORMS: the default entry -- plain and typed-key passes on the persistent kernel, peer-scatter and key-value passes on
-// onesweep_lpc32_kernel (same tile size, same workspace layout and look-back protocol).
-template <int RB, int WARPS, int ITEMS, int MINB, int LB, int CLR = 0, int NOB5 = 0, bool WITH_FORMS = false, bool TRACE = false>
+// FORMS: 0 = plain passes only (tuning variants); 1 = the r = 8 default entry: plain and typed-key passes on the persistent
+// kernel, peer-scatter and key-value passes on onesweep_lpc32_kernel (same tile size, workspace layout and look-back protocol);
+// 2 = plain and typed-key passes (the r < 8 default entries; key-value sorts there use the warp-multisplit entries).
+template <int RB, int WARPS, int ITEMS, int MINB, int LB, int CLR = 0, int NOB5 = 0, int FORMS = 0, bool TRACE = false>
 constexpr OnesweepLauncher make_lpc3_launcher()
 {
     using S_ = Lpc32Shape<RB, WARPS, ITEMS>;
-    if constexpr (WITH_FORMS)
+    if constexpr (FORMS == 1)
         return OnesweepLauncher{RB, S_::THREADS, ITEMS, kModeLpc3, (uint32_t)S_::TILE, S_::PORTION_MAX, S_::SMEM_BYTES,
                                 &onesweep_lpc3_launch<RB, WARPS, ITEMS, MINB, LB, CLR, NOB5>,
                                 &onesweep_lpc32_launch<RB, WARPS, ITEMS, MINB, LB, 5, kPassPeer, false>,
                                 &onesweep_lpc32_launch<RB, WARPS, ITEMS, MINB, LB, 5, kPassPairs, false>,
                                 &onesweep_lpc3_launch<RB, WARPS, ITEMS, MINB, LB, CLR, NOB5, true>,
                                 &onesweep_lpc32_launch<RB, WARPS, ITEMS, MINB, LB, 5, kPassPairsTyped, false>};
+    else if constexpr (FORMS == 2)
+        return OnesweepLauncher{RB, S_::THREADS, ITEMS, kModeLpc3, (uint32_t)S_::TILE, S_::PORTION_MAX, S_::SMEM_BYTES,
+                                &onesweep_lpc3_launch<RB, WARPS, ITEMS, MINB, LB, CLR, NOB5>, nullptr, nullptr,
+                                &onesweep_lpc3_launch<RB, WARPS, ITEMS, MINB, LB, CLR, NOB5, true>, nullptr};
     else
         return OnesweepLauncher{RB, S_::THREADS, ITEMS, kModeLpc3, (uint32_t)S_::TILE, S_::PORTION_MAX, S_::SMEM_BYTES,
                                 &onesweep_lpc3_launch<RB, WARPS, ITEMS, MINB, LB, CLR, NOB5, false, TRACE>, nullptr, nullptr, nullptr,

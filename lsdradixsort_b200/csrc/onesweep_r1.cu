@@ -1,9 +1,10 @@
 // onesweep_r1.cu -- kernel shapes for 1-bit digits (32 passes).  Entry 0 is the default.
-#include "onesweep.cuh"
+#include "onesweep_lpc3.cuh"
 
 namespace lsd {
 
 static const OnesweepLauncher kTable[] = {
+    make_lpc3_launcher<1, 9, 29, 3, 4, 0, 1, 2>(),  // 0: default for plain / typed-key sorts -- persistent LPC pass (run-time shift, dedicated prefetch buffer)
     make_launcher<1, 256, 16, kMatchBallot, true>(),
     make_launcher<1, 128, 16, kMatchBallot, true>(),
     make_launcher<1, 512, 16, kMatchBallot, true>(),

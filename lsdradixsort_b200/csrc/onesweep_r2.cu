@@ -1,9 +1,10 @@
 // onesweep_r2.cu -- kernel shapes for 2-bit digits (16 passes).  Entry 0 is the default.
-#include "onesweep.cuh"
+#include "onesweep_lpc3.cuh"
 
 namespace lsd {
 
 static const OnesweepLauncher kTable[] = {
+    make_lpc3_launcher<2, 9, 29, 3, 4, 0, 1, 2>(),  // 0: default for plain / typed-key sorts -- persistent LPC pass (run-time shift, dedicated prefetch buffer)
     make_launcher<2, 256, 16, kMatchBallot, true>(),
     make_launcher<2, 128, 16, kMatchBallot, true>(),
     make_launcher<2, 512, 16, kMatchBallot, true>(),

@@ -1,9 +1,10 @@
 // onesweep_r4.cu -- kernel shapes for 4-bit digits (8 passes).  Entry 0 is the default.
-#include "onesweep.cuh"
+#include "onesweep_lpc3.cuh"
 
 namespace lsd {
 
 static const OnesweepLauncher kTable[] = {
+    make_lpc3_launcher<4, 9, 29, 3, 4, 0, 1, 2>(),  // 0: default for plain / typed-key sorts -- persistent LPC pass (run-time shift, dedicated prefetch buffer)
     make_launcher<4, 256, 16, kMatchBallot, true>(),
     make_launcher<4, 128, 16, kMatchBallot, true>(),
     make_launcher<4, 512, 16, kMatchBallot, true>(),

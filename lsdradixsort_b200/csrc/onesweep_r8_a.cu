@@ -8,7 +8,7 @@
 namespace lsd {
 
 static const OnesweepLauncher kPart[] = {
-    make_lpc3_launcher<8, 9, 29, 3, 4, 0, 1, true>(),  // 0: default -- persistent LPC32 pass, next tile prefetched into the dead counter matrix, ticket hand-over by mbarrier (= variant 75); peer-scatter / key-value / typed-key passes on onesweep_lpc32_kernel (= variant 68)
+    make_lpc3_launcher<8, 9, 29, 3, 4, 0, 1, 1>(),  // 0: default -- persistent LPC32 pass, next tile prefetched into the dead counter matrix, ticket hand-over by mbarrier (= variant 75); peer-scatter / key-value / typed-key passes on onesweep_lpc32_kernel (= variant 68)
     make_launcher<8, 128, 24, kMatchBallot>(),   // 1
     make_launcher<8, 256, 24, kMatchBallot, true>(),   // 2
     make_launcher<8, 1024, 8, kMatchBallot>(),   // 3

@@ -31,7 +31,7 @@ static const OnesweepLauncher kPart[] = {
     make_lpc3_launcher<8, 9, 29, 3, 4, 0, 1>(),          // 75: as 70, ticket handed over through an mbarrier (no end-of-tile barrier)
     make_lpc3_launcher<8, 9, 29, 3, 4, 2, 0>(),          // 76: as 70, matrix zero-filled by a TMA copy of a zero page
     make_lpc3_launcher<8, 9, 29, 3, 4, 2, 1>(),          // 77: both
-    make_lpc3_launcher<8, 9, 29, 3, 4, 0, 1, false, true>(),  // 78: as 75 with the per-tile phase trace compiled in (bench_tools/trace.py --variant 78)
+    make_lpc3_launcher<8, 9, 29, 3, 4, 0, 1, 0, true>(),  // 78: as 75 with the per-tile phase trace compiled in (bench_tools/trace.py --variant 78)
 };
 
 const OnesweepLauncher* onesweep_r8_part_c(int* count)

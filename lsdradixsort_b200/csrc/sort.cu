@@ -108,7 +108,11 @@ const OnesweepLauncher* select_launcher(int r, int block, uint32_t variant, bool
     const OnesweepLauncher* t = table_for(r, &count);
     if (!t) return nullptr;
     if (variant != 0) return variant < (uint32_t)count ? &t[variant] : nullptr;
-    if (block <= 0) return &t[0];  // entry 0 of every table has every form
+    if (block <= 0) {  // the first entry that has the requested form (entry 0 has every form for r = 8; for r < 8 the key-value
+        for (int i = 0; i < count; ++i)  // forms live in the warp-multisplit entries behind it)
+            if (pass_fn(t[i], pairs, typed)) return &t[i];
+        return nullptr;
+    }
     // `block` is the reference's threads-per-block knob: pick the warp-multisplit shape with exactly that many
     // threads if there is one, else the shape (of any family) whose CTA size is closest.
     const OnesweepLauncher* best = nullptr;
