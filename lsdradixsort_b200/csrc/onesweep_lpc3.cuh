@@ -157,6 +157,12 @@ onesweep_lpc3_kernel(const PassArgs a)
         if (warp == 0) LSD_TRACE(3);
 
         uint32_t* lb_row = a.lookback + (size_t)tile * H;
+        // Pull this tile's still empty look-back record into L2 now.  The successors poll it before it is published, and
+        // the lines zeroed at the start of the sort were evicted by the key stream long ago: without this their first
+        // polls go to DRAM (measured: 0.663 -> 0.646 ms per pass).
+        // (r = 8 only: with the 64-byte records of r = 4 it made the pass 5 % slower, 0.537 -> 0.567 ms)
+        if constexpr (H >= 256)
+            if (tid < (uint32_t)H / 8) asm volatile("prefetch.global.L2 [%0];" ::"l"(lb_row + 8 * tid));  // one per 32-byte sector
 
         if (warp < (uint32_t)SW) {
             // ================= scan warps: totals -> bucket starts -> exclusive lane prefix =================

@@ -198,6 +198,8 @@ onesweep_lpc32_kernel(const PassArgs a)
     if (warp == 0) LSD_TRACE(3);  // count barrier passed
 
     uint32_t* lb_row = a.lookback + (size_t)tile * H;
+    // pull this tile's still empty look-back record into L2: successors poll it before it is published (see onesweep_lpc3.cuh)
+    if (tid < (uint32_t)(H + 7) / 8) asm volatile("prefetch.global.L2 [%0];" ::"l"(lb_row + 8 * tid));  // one per 32-byte sector
 
     if constexpr (SP) {
         // ================= single-pass scan: warps 0..7, one matrix row per thread, the row stays in registers
