@@ -190,12 +190,13 @@ __device__ __forceinline__ uint4 lds128_volatile(const uint32_t* p)
     return v;
 }
 
-template <int THREADS>
+// TRACE: phase clocks per tile (LSD_SCAN_TRACE=1); compile-time so that the shipped kernel carries no run-time checks
+template <int THREADS, bool TRACE = false>
 __global__ void __launch_bounds__(THREADS)
 scan_tma_kernel(uint32_t* __restrict__ a, uint64_t n, ScanWorkspace* __restrict__ ws, uint32_t* __restrict__ trace)
 {
-    const long long t_start = trace ? clock64() : 0;
-#define SCAN_TRACE(slot) do { if (trace && tid == 0) trace[(size_t)tile * 8 + (slot)] = (uint32_t)(clock64() - t_start); } while (0)
+    const long long t_start = (TRACE && trace) ? clock64() : 0;
+#define SCAN_TRACE(slot) do { if constexpr (TRACE) if (trace && tid == 0) trace[(size_t)tile * 8 + (slot)] = (uint32_t)(clock64() - t_start); } while (0)
     constexpr int WARPS = THREADS / 32;
     constexpr int TILE = THREADS * kScanItems;
     constexpr int P = kScanVecs * WARPS;
@@ -217,7 +218,8 @@ scan_tma_kernel(uint32_t* __restrict__ a, uint64_t n, ScanWorkspace* __restrict_
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         const uint32_t t = atomicAdd(&ws->ticket, 1u);
         s_tile = t;
-        if (trace) trace[(size_t)t * 8 + 0] = (uint32_t)(clock64() - t_start);
+        if constexpr (TRACE)
+            if (trace) trace[(size_t)t * 8 + 0] = (uint32_t)(clock64() - t_start);
         const uint64_t b = (uint64_t)t * TILE;
         if (n - b >= (uint64_t)TILE) {
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(scan_smem_u32(&s_bar)), "r"(TILE * 4) : "memory");
@@ -583,14 +585,29 @@ int launch_prefix_sum(uint32_t* a, uint64_t n, int block, void* ws, size_t ws_by
     if (tma) {
         switch (threads) {
             case 128:
+                if (trace) {
+                    LSD_CUDA_TRY(cudaFuncSetAttribute(scan_tma_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                    scan_tma_kernel<128, true><<<(unsigned)tiles, 128, smem, s>>>(a, n, w, trace);
+                    break;
+                }
                 LSD_CUDA_TRY(cudaFuncSetAttribute(scan_tma_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 scan_tma_kernel<128><<<(unsigned)tiles, 128, smem, s>>>(a, n, w, trace);
                 break;
             case 256:
+                if (trace) {
+                    LSD_CUDA_TRY(cudaFuncSetAttribute(scan_tma_kernel<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                    scan_tma_kernel<256, true><<<(unsigned)tiles, 256, smem, s>>>(a, n, w, trace);
+                    break;
+                }
                 LSD_CUDA_TRY(cudaFuncSetAttribute(scan_tma_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 scan_tma_kernel<256><<<(unsigned)tiles, 256, smem, s>>>(a, n, w, trace);
                 break;
             default:
+                if (trace) {
+                    LSD_CUDA_TRY(cudaFuncSetAttribute(scan_tma_kernel<512, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                    scan_tma_kernel<512, true><<<(unsigned)tiles, 512, smem, s>>>(a, n, w, trace);
+                    break;
+                }
                 LSD_CUDA_TRY(cudaFuncSetAttribute(scan_tma_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 scan_tma_kernel<512><<<(unsigned)tiles, 512, smem, s>>>(a, n, w, trace);
                 break;
