@@ -338,6 +338,147 @@ scan_tma_kernel(uint32_t* __restrict__ a, uint64_t n, ScanWorkspace* __restrict_
 }
 
 // -------------------------------------------------------------------------------------
+// scan_l2_kernel: reduce-then-scan per chunk, the second read served by the 126 MB L2.
+//
+// Why (profiles/r01_scan_variants.txt): scan_tma_kernel is bound by the shared memory its WAITING tiles occupy -- a tile
+// lives ~26 K cycles, 13 K of them in the look-back walk, with its 32 KiB parked in shared memory, so ~33 MB are in flight
+// and throughput = bytes in flight / tile life.  Here a CTA reads its chunk (THREADS x 4*VECS elements, 64 KiB) once to
+// get the chunk total and its threads' running sums, publishes the total, walks the look-back chain holding NOTHING but
+// VECS registers per thread, then reads the chunk again -- from L2, where the first read left it a few microseconds
+// earlier -- and writes the results.  DRAM traffic stays 8 B per element as long as L2 keeps the chunks in flight
+// (~6 CTAs per SM x 64 KiB = 57 MB).
+// -------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 ld_l2_v4(const uint4* p)
+{
+    uint4 v;
+    asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
+}
+
+template <int THREADS, int VECS>
+__global__ void __launch_bounds__(THREADS)
+scan_l2_kernel(uint32_t* __restrict__ a, uint64_t n, ScanWorkspace* __restrict__ ws)
+{
+    constexpr int WARPS = THREADS / 32;
+    constexpr int CHUNK = THREADS * VECS * 4;
+    constexpr int P = VECS * WARPS;
+    constexpr int PPL = P / 32;
+    static_assert(P % 32 == 0 && PPL >= 1, "partials must fill warp 0 evenly");
+
+    __shared__ uint32_t s_tile;
+    __shared__ uint32_t s_partial[P];
+    __shared__ uint32_t s_tile_prefix;
+
+    const uint32_t tid = threadIdx.x;
+    const uint32_t lane = tid & 31u;
+    const uint32_t warp = tid >> 5;
+
+    if (tid == 0) s_tile = atomicAdd(&ws->ticket, 1u);
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const uint64_t base = (uint64_t)tile * CHUNK;
+    const uint64_t left = n - base;
+    const bool full = left >= (uint64_t)CHUNK;
+    const uint4* src = reinterpret_cast<const uint4*>(a + base);
+
+    auto load_vec = [&](int j) -> uint4 {
+        const uint32_t idx = (uint32_t)j * THREADS + tid;
+        if (full) return ld_l2_v4(src + idx);
+        const uint64_t e = 4ull * idx;
+        uint4 v;
+        v.x = e + 0 < left ? a[base + e + 0] : 0u;
+        v.y = e + 1 < left ? a[base + e + 1] : 0u;
+        v.z = e + 2 < left ? a[base + e + 2] : 0u;
+        v.w = e + 3 < left ? a[base + e + 3] : 0u;
+        return v;
+    };
+
+    // ---- first read: per-vector sums, warp scans ----
+    uint32_t excl[VECS];
+#pragma unroll
+    for (int j = 0; j < VECS; ++j) {
+        const uint4 v = load_vec(j);
+        const uint32_t sum = v.x + v.y + v.z + v.w;
+        const uint32_t incl = warp_inclusive_scan(sum, lane);
+        excl[j] = incl - sum;
+        if (lane == 31) s_partial[j * WARPS + warp] = incl;
+    }
+    __syncthreads();
+
+    if (warp == 0) {
+        uint32_t part[PPL];
+        uint32_t lane_sum = 0;
+#pragma unroll
+        for (int k = 0; k < PPL; ++k) {
+            part[k] = s_partial[lane * PPL + k];
+            lane_sum += part[k];
+        }
+        const uint32_t lane_incl = warp_inclusive_scan(lane_sum, lane);
+        const uint32_t tile_total = __shfl_sync(kFullMask, lane_incl, 31);
+        uint32_t run = lane_incl - lane_sum;
+#pragma unroll
+        for (int k = 0; k < PPL; ++k) {
+            s_partial[lane * PPL + k] = run;
+            run += part[k];
+        }
+        uint32_t exclusive = 0;
+        if (tile == 0) {
+            if (lane == 0) st_relaxed_gpu(&ws->state[0], kFlagInclusive | tile_total);
+        } else {
+            if (lane == 0) st_relaxed_gpu(&ws->state[tile], kFlagAggregate | tile_total);
+            int64_t look = (int64_t)tile - 1;
+            while (true) {
+                const int64_t idx = look - (int64_t)lane;
+                const uint64_t w = idx >= 0 ? ld_relaxed_gpu(&ws->state[idx]) : kFlagInclusive;  // virtual chunks: prefix 0
+                const uint32_t ready = __ballot_sync(kFullMask, (w >> 32) != 0);
+                const uint32_t incl_mask = __ballot_sync(kFullMask, (w >> 32) == 2);
+                uint32_t take = (uint32_t)w;
+                bool finished = false;
+                if (incl_mask) {
+                    const uint32_t first = __ffs(incl_mask) - 1;
+                    const uint32_t need = (2u << first) - 1u;
+                    if ((ready & need) != need) continue;
+                    if (lane > first) take = 0;
+                    finished = true;
+                } else if (ready != kFullMask) {
+                    continue;
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) take += __shfl_xor_sync(kFullMask, take, o);
+                exclusive += take;
+                if (finished) break;
+                look -= 32;
+            }
+            if (lane == 0) st_relaxed_gpu(&ws->state[tile], kFlagInclusive | (uint32_t)(exclusive + tile_total));
+        }
+        if (lane == 0) s_tile_prefix = exclusive;
+    }
+    __syncthreads();
+
+    // ---- second read (L2), exclusive results, streaming stores ----
+    const uint32_t tile_prefix = s_tile_prefix;
+#pragma unroll
+    for (int j = 0; j < VECS; ++j) {
+        const uint4 v = load_vec(j);
+        uint32_t run = tile_prefix + s_partial[j * WARPS + warp] + excl[j];
+        uint4 o;
+        o.x = run; run += v.x;
+        o.y = run; run += v.y;
+        o.z = run; run += v.z;
+        o.w = run;
+        const uint64_t e = 4ull * ((uint32_t)j * THREADS + tid);
+        if (full) {
+            __stcs(reinterpret_cast<uint4*>(a + base + e), o);
+        } else {
+            if (e + 0 < left) a[base + e + 0] = o.x;
+            if (e + 1 < left) a[base + e + 1] = o.y;
+            if (e + 2 < left) a[base + e + 2] = o.z;
+            if (e + 3 < left) a[base + e + 3] = o.w;
+        }
+    }
+}
+
+// -------------------------------------------------------------------------------------
 // scan_cluster_kernel: scan_tma_kernel with thread-block clusters of 8 CTAs sharing ONE look-back record.
 //
 // Why (profiles/r01_scan_variants.txt): with ~900 tiles in flight every tile's look-back walks ~18 windows of 32
@@ -538,6 +679,7 @@ static int scan_threads_for(int block)
 }
 
 // LSD_SCAN_TRACE=1 (tuning aid): 8 uint32 phase clocks per tile are written after the tile states
+static const bool g_scan_l2 = [] { const char* e = getenv("LSD_SCAN_L2"); return e && e[0] == '1'; }();
 static const bool g_scan_trace = [] { const char* e = getenv("LSD_SCAN_TRACE"); return e && e[0] == '1'; }();
 
 size_t scan_workspace_bytes(uint64_t n, int block)
@@ -558,6 +700,15 @@ int launch_prefix_sum(uint32_t* a, uint64_t n, int block, void* ws, size_t ws_by
     if (tiles > 0x7FFFFFFFull) return LSD_ERR_UNSUPPORTED;
     LSD_CUDA_TRY(cudaMemsetAsync(ws, 0, need, s));
     auto* w = static_cast<ScanWorkspace*>(ws);
+    if (g_scan_l2 && aligned_to(a, 16)) {
+        // 256 threads x 64 elements = 64 KiB chunks: fewer records than the workspace was sized for
+        constexpr int kL2Threads = 256, kL2Vecs = 16;
+        const uint64_t chunk = (uint64_t)kL2Threads * kL2Vecs * 4;
+        const uint64_t chunks = (n + chunk - 1) / chunk;
+        scan_l2_kernel<kL2Threads, kL2Vecs><<<(unsigned)chunks, kL2Threads, 0, s>>>(a, n, w);
+        LSD_LAUNCH_CHECK();
+        return LSD_OK;
+    }
     const bool tma = !g_scan_register_path && aligned_to(a, 16);
     uint32_t* trace_c = g_scan_trace ? reinterpret_cast<uint32_t*>(static_cast<ScanWorkspace*>(ws)->state + tiles) : nullptr;
     if (tma && !g_scan_no_cluster) {
