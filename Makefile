@@ -7,7 +7,7 @@ GENCODE := -gencode arch=compute_100a,code=sm_100a
 NVFLAGS := -O3 -std=c++17 -lineinfo $(GENCODE) -Xcompiler -fPIC -Xcompiler -fvisibility=hidden --expt-relaxed-constexpr
 CSRC    := lsdradixsort_b200/csrc
 OBJDIR  := build/obj
-SRCS    := api.cu sort.cu histogram.cu scan.cu onesweep_r1.cu onesweep_r2.cu onesweep_r4.cu onesweep_r8.cu onesweep_r8_a.cu onesweep_r8_b.cu onesweep_r8_c.cu
+SRCS    := api.cu sort.cu histogram.cu scan.cu onesweep_r1.cu onesweep_r2.cu onesweep_r4.cu onesweep_r8.cu onesweep_r8_a.cu onesweep_r8_b.cu onesweep_r8_c.cu onesweep_r8_d.cu
 OBJS    := $(addprefix $(OBJDIR)/,$(SRCS:.cu=.o))
 LIB     := lsdradixsort_b200/liblsdsort.so
 

@@ -14,7 +14,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--log2n", type=int, default=28)
 ap.add_argument("--variant", type=int, default=19)
 ap.add_argument("--tile", type=int, default=8352)
-ap.add_argument("--family", type=str, default="lpc", choices=["lpc", "cpc", "cpcp"])
+ap.add_argument("--family", type=str, default="lpc", choices=["lpc", "cpc", "cpcp", "wide"])
 args = ap.parse_args()
 n = 1 << args.log2n
 g = torch.Generator(device="cuda").manual_seed(0)
@@ -32,11 +32,16 @@ t = t[200:-200]  # steady state
 names = {0: "ticket+clear", 1: "tile landed", 2: "w0 counted", 3: "count barrier", 4: "scan1+digit scan", 5: "scan2 done",
          6: "w0 ranked", 7: "w0 scattered", 8: "lookback start", 9: "lookback done", 10: "chain complete", 13: "lookback rounds", 14: "lookback hops",
          11: "final barrier", 12: "w0 stores issued"}
+if args.family == "wide":
+    names = {1: "tile landed", 2: "w0 counted", 3: "count barrier", 4: "scan1+digit scan", 5: "scan2 done", 6: "w0 ranked+scattered",
+             7: "barrier C passed", 8: "lookback start", 9: "lookback done", 10: "chain tail (last warp)", 11: "chain tail (last-1)",
+             12: "w0 stores issued", 13: "lookback rounds", 14: "lookback hops", 15: "lookback load wait (sum)", 0: "lookback processing (sum)"}
 if args.family == "cpc":
     names = {0: "ticket+clear", 1: "tile landed", 2: "w0 ranked", 3: "rank barrier", 4: "scan+Q done", 5: "positions done",
              6: "w0 scattered", 7: "lookback done", 8: "final barrier", 9: "w0 stores issued", 10: "ticket returned", 11: "w2 clear done", 13: "lookback rounds",
              14: "lookback hops"}
 print("pass ms", st)
+print("tile period per SM (cycles):", st[1] * 1e-3 * 1.965e9 * 148 / tiles)
 for k in sorted(names):
     col = t[:, k]
     col = col[col > 0]

@@ -12,12 +12,13 @@ namespace lsd {
 const OnesweepLauncher* onesweep_r8_part_a(int* count);
 const OnesweepLauncher* onesweep_r8_part_b(int* count);
 const OnesweepLauncher* onesweep_r8_part_c(int* count);
+const OnesweepLauncher* onesweep_r8_part_d(int* count);
 
 const OnesweepLauncher* onesweep_table_r8(int* count)
 {
     static const std::vector<OnesweepLauncher> table = [] {  // thread-safe one-time concatenation
         std::vector<OnesweepLauncher> t;
-        for (auto part : {&onesweep_r8_part_a, &onesweep_r8_part_b, &onesweep_r8_part_c}) {
+        for (auto part : {&onesweep_r8_part_a, &onesweep_r8_part_b, &onesweep_r8_part_c, &onesweep_r8_part_d}) {
             int n = 0;
             const OnesweepLauncher* p = part(&n);
             t.insert(t.end(), p, p + n);
