@@ -48,6 +48,8 @@ def parse_args():
     ap.add_argument("--exchange", choices=["peer", "nccl"], default="peer",
                     help="N>1: fused partition+exchange over NVLink peer stores (default) or partition + NCCL all_to_all")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-reference-gpu", action="store_true",
+                    help="skip the reference_gpu block (the reference's CUDA kernels from oracle/_ref on the same keys)")
     ap.add_argument("--cpu-baseline-log2n", type=int, default=28)
     return ap.parse_args()
 
@@ -196,15 +198,28 @@ def ncu_traffic(kernel_key: str):
     return None
 
 
-def cpu_reference_sort_gkeys(log2n: int, reps: int = 1):
-    """Time the reference's CPU LSDRadixSort (r=8) on 2^log2n uniform keys.  Returns (Gkeys/s, kind)."""
+def host_uniform_keys(n: int, seed: int = 0):
+    """keygen.uniform_u32 in 2^26-key pieces (same values, bounded temporaries)."""
+    import numpy as np
+
+    from lsdradixsort_b200 import keygen
+
+    out = np.empty(n, dtype=np.uint32)
+    step = 1 << 26
+    for off in range(0, n, step):
+        out[off:off + step] = keygen.uniform_u32(min(step, n - off), seed, offset=off)
+    return out
+
+
+def cpu_reference_sort_gkeys(log2n: int, reps: int = 1, keys=None, return_sorted: bool = False):
+    """Time the reference's CPU LSDRadixSort (r=8) on 2^log2n uniform keys (or on `keys`).  Returns (Gkeys/s, kind[, sorted])."""
     import numpy as np
 
     import _oracle
-    from lsdradixsort_b200 import keygen
 
-    n = 1 << log2n
-    keys = keygen.uniform_u32(n, seed=0)
+    if keys is None:
+        keys = host_uniform_keys(1 << log2n, seed=0)
+    n = keys.size
     ref = _oracle.ref()
     best = None
     for _ in range(reps):
@@ -217,7 +232,53 @@ def cpu_reference_sort_gkeys(log2n: int, reps: int = 1):
         dt = time.perf_counter() - t0
         best = dt if best is None else min(best, dt)
     assert bool(np.all(b[:-1] <= b[1:])), "CPU reference produced an unsorted array"
-    return n / best / 1e9, ("reference" if ref is not None else "port")
+    kind = "reference" if ref is not None else "port"
+    return (n / best / 1e9, kind, b) if return_sorted else (n / best / 1e9, kind)
+
+
+def reference_gpu_block(src, expected, n: int):
+    """The reference's own CUDA kernels (GPULSDRadixSort, LSDRadixSort.cu:839-910, rebuilt unmodified for sm_100a into
+    oracle/_ref) on the same keys, same GPU: a reported baseline beside the headline, not a target.  Called past the
+    harness's aux > input SKIP (.cu:940-951), with its preconditions met (count % block == 0, G * 2^r < 2^31)."""
+    import torch
+
+    import _oracle
+
+    ref = _oracle.ref()
+    if ref is None:
+        return {"unavailable": "oracle/_ref/libref_lsd.so not built (needs /root/reference at build time)"}
+    rows = []
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for r, block in ((8, 256), (8, 1024), (4, 512)):
+        grid = n // block
+        if n % block or grid * (1 << r) >= 2**31:
+            rows.append({"r": r, "block": block, "skipped": "reference precondition (count % block, G*2^r < 2^31)"})
+            continue
+        try:
+            a, b = torch.empty_like(src), torch.empty_like(src)
+            h = torch.empty(3 * grid * (1 << r), dtype=torch.int32, device=src.device)
+            bs = torch.empty(ref.ref_block_sums_count(grid * (1 << r), block) + 64, dtype=torch.int32, device=src.device)
+            ts = []
+            for _ in range(3):
+                a.copy_(src)
+                torch.cuda.synchronize()
+                ev0.record()
+                rc = ref.ref_gpu_sort(a.data_ptr(), b.data_ptr(), h.data_ptr(), bs.data_ptr(), n, block, r)
+                ev1.record()
+                torch.cuda.synchronize()
+                if rc != 0:
+                    raise RuntimeError(f"cuda error {rc}")
+                ts.append(ev0.elapsed_time(ev1))
+            ms = min(ts[1:])
+            rows.append({"r": r, "block": block, "ms": round(ms, 3), "gkeys_s": round(n / ms / 1e6, 3),
+                         "frac_of_hbm_roofline": round((32 // r) * 8.0 * n / (ms * 1e6) / measured_peak()[0], 4),
+                         "bit_identical_to_ours": bool(torch.equal(a, expected))})
+            del a, b, h, bs
+        except Exception as e:  # noqa: BLE001
+            rows.append({"r": r, "block": block, "error": str(e)[:200]})
+    return {"what": "reference GPULSDRadixSort (LSDRadixSort.cu:839-910) rebuilt with nvcc for sm_100a, unmodified, "
+                    "same keys, same B200, CUDA events around the call, best of 2 after a warm-up",
+            "keys": n, "runs": rows}
 
 
 # ----------------------------------------------------------------------------------------------
@@ -256,6 +317,7 @@ def run_reference(args):
 # our arm
 # ----------------------------------------------------------------------------------------------
 def run_ours(args):
+    import numpy as np
     import torch
     import torch.distributed as dist
 
@@ -289,13 +351,33 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    g = torch.Generator(device=dev).manual_seed(1234 + rank)
-    src = torch.empty(n_local, dtype=torch.int32, device=dev)
-    chunk = 1 << 26
-    for lo in range(0, n_local, chunk):  # bounded temporaries: randint works in int64
-        hi = min(n_local, lo + chunk)
-        src[lo:hi] = torch.randint(-(2**31), 2**31, (hi - lo,), dtype=torch.int64, device=dev, generator=g).to(torch.int32)
+    host_keys = None
+    if not distributed:
+        # the SAME keys go to the GPU arm, to the e2e leg and to the reference's CPU sort (cpu_baseline): the bench line is
+        # only printed if the GPU result is bit-identical to the reference's (CheckArrays, LSDRadixSort.cu:1018)
+        import numpy as np
+
+        host_keys = host_uniform_keys(n_local, seed=0)
+        src = torch.from_numpy(host_keys.view(np.int32)).to(dev)
+    else:
+        g = torch.Generator(device=dev).manual_seed(1234 + rank)
+        src = torch.empty(n_local, dtype=torch.int32, device=dev)
+        chunk = 1 << 26
+        for lo in range(0, n_local, chunk):  # bounded temporaries: randint works in int64
+            hi = min(n_local, lo + chunk)
+            src[lo:hi] = torch.randint(-(2**31), 2**31, (hi - lo,), dtype=torch.int64, device=dev, generator=g).to(torch.int32)
     work = torch.empty_like(src)
+
+    def fingerprint(t):
+        """Order-independent fingerprint of a key multiset: the 4 x 256 digit histograms + 64-bit sum and sum of squares."""
+        h = L.digit_histograms(t, R_BITS).to(torch.int64).reshape(-1) if t.numel() else torch.zeros(4 * 256, dtype=torch.int64, device=dev)
+        acc = torch.zeros(2, dtype=torch.int64, device=dev)
+        step_keys = 1 << 27
+        for lo in range(0, t.numel(), step_keys):
+            u = t[lo:lo + step_keys].to(torch.int64) & 0xFFFFFFFF
+            acc[0] += u.sum()
+            acc[1] += (u * u).sum()  # wraps mod 2^64
+        return torch.cat([h, acc])
 
     if distributed:
         capacity = int(n_local * 1.25) + (1 << 16)
@@ -330,6 +412,9 @@ def run_ours(args):
     for i in range(args.steps):
         work.copy_(src)  # restore the unsorted input (not timed; 2 x n x 4 B also flushes nothing we rely on:
         if distributed:  # the key buffers are far larger than the 126 MB L2)
+            # poison the receive buffer: every step re-sorts the same keys, so without this a lost peer store would leave
+            # the previous step's (identical, correct) key in place and the check below could not see it
+            recv.fill_(0x5A5A5A5A - (1 << 32) + i)
             dist.barrier()
         ev0[i].record()
         out, stats = step()
@@ -355,6 +440,12 @@ def run_ours(args):
         return True
 
     ok = is_sorted_u32(out)
+    fp_in, fp_out = fingerprint(src), fingerprint(out)
+    if distributed:
+        dist.all_reduce(fp_in, op=dist.ReduceOp.SUM)
+        dist.all_reduce(fp_out, op=dist.ReduceOp.SUM)
+    same_multiset = bool(torch.equal(fp_in, fp_out))
+    ok = ok and same_multiset
     if distributed:
         lo = int(out[0].item()) & 0xFFFFFFFF if out.numel() else 0
         hi = int(out[-1].item()) & 0xFFFFFFFF if out.numel() else 0
@@ -368,7 +459,7 @@ def run_ours(args):
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         ok = bool(flag.item())
     if not ok:
-        raise SystemExit("bench.py: output is NOT sorted -- refusing to report a number")
+        raise SystemExit("bench.py: output is NOT the sorted input (order, rank boundaries or key multiset) -- refusing to report a number")
 
     # ---- roofline leg: per-kernel CUDA-event times of the local sort (same keys, same shapes) ----
     peak, peak_src = measured_peak()
@@ -389,9 +480,14 @@ def run_ours(args):
         "bound": "hbm", "kernel": "onesweep digit pass (r=8), the dominant kernel: 4 launches per sort",
         "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
         "peak_source": peak_src, "algorithmic_bytes_per_launch": 8 * n_roof, "avg_launch_ms": round(avg_pass, 4),
-        "traffic": traffic, "hist_plus_plan_ms": round(avg_hist, 4),
+        "frac_of_nominal_8TBs": round(achieved / 8000.0, 4),
+        "traffic": traffic if not distributed else None,
+        "traffic_note": ("dram__bytes_read+write per launch from the committed ncu --set full capture of this kernel at 2^28 keys"
+                         if not distributed else "the committed ncu capture is of a 2^28-key launch; not scaled to this launch size"),
+        "hist_plus_plan_ms": round(avg_hist, 4),
         "whole_sort": {"algorithmic_bytes": 32 * n_roof, "ms": round(sort_ms, 4),
-                       "frac_of_peak": round(32.0 * n_roof / (sort_ms * 1e6) / peak, 4) if sort_ms > 0 else None},
+                       "frac_of_peak": round(32.0 * n_roof / (sort_ms * 1e6) / peak, 4) if sort_ms > 0 else None,
+                       "frac_of_nominal_8TBs": round(32.0 * n_roof / (sort_ms * 1e6) / 8000.0, 4) if sort_ms > 0 else None},
     }
     launches_per_sort = sorter.info(n_roof).launches
     per_step = launches_per_sort
@@ -423,7 +519,7 @@ def run_ours(args):
     e2e = None
     if not distributed:
         hs = L.HostSorter(n_local, r=R_BITS, block=args.block)
-        pinned_src = src.cpu().pin_memory()
+        pinned_src = torch.from_numpy(host_keys.view(np.int32)).pin_memory()
         pinned = torch.empty_like(pinned_src).pin_memory()
         e2e_steps = max(1, min(args.steps, 10))
         ts = []
@@ -462,12 +558,26 @@ def run_ours(args):
                "api": "multi.distributed_sort with pinned host buffers per rank", "timer": "CUDA events, max over ranks"}
 
     cpu_baseline = None
+    parity = {"sorted": True, "same_key_multiset_as_input": same_multiset}
     if rank == 0 and not distributed and not args.no_cpu_baseline:
-        gk, kind = cpu_reference_sort_gkeys(args.cpu_baseline_log2n)
+        sample_n = min(n_local, 1 << args.cpu_baseline_log2n)
+        gk, kind, want = cpu_reference_sort_gkeys(0, keys=host_keys[:sample_n], return_sorted=True)
         cpu_baseline = {"value": round(gk, 5), "unit": UNIT, "cores": 1, "kind": kind,
-                        "sample": f"2^{args.cpu_baseline_log2n} uniform uint32 keys, 1 run of the reference's CPU LSDRadixSort "
-                                  "(r=8, LSDRadixSort.cu:62-69; single-threaded as written)",
+                        "sample": f"{sample_n} uniform uint32 keys (the GPU arm's own input), 1 run of the reference's CPU "
+                                  "LSDRadixSort (r=8, LSDRadixSort.cu:62-69; single-threaded as written)",
                         "host_cores_available": os.cpu_count()}
+        if sample_n == n_local:
+            # CheckArrays (.cu:1018): the GPU sort of the timed region against the reference's CPU sort of the same keys
+            exact = bool(np.array_equal(out.cpu().numpy().view(np.uint32), want))
+            e2e_exact = bool(np.array_equal(pinned.numpy().view(np.uint32), want))
+            parity.update({"bit_exact_vs_reference_cpu_sort": exact, "e2e_bit_exact_vs_reference_cpu_sort": e2e_exact,
+                           "reference_kind": kind, "keys": n_local})
+            if not (exact and e2e_exact):
+                raise SystemExit("bench.py: GPU result differs from the reference's CPU sort of the same keys")
+        del want
+    reference_gpu = None
+    if rank == 0 and not distributed and not args.no_reference_gpu:
+        reference_gpu = reference_gpu_block(src, out, n_local)
 
     if rank == 0:
         line = {
@@ -480,8 +590,10 @@ def run_ours(args):
                        "timing": "CUDA events around each step on the launching stream, mean over steps, max over ranks",
                        "published_reference": "0.400 Gkeys/s (RTX 3060 Ti, 2^30 keys, R=4/B=512; BenchmarkLSDRadixSort.md:153-161)"},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": gpu_launches,
-            "clocks": clocks, "verified_sorted": True,
+            "clocks": clocks, "verified_sorted": True, "parity": parity,
         }
+        if reference_gpu is not None:
+            line["reference_gpu"] = reference_gpu
         if stats is not None:
             line["exchange"] = dict(exchange or {}, sent_bytes_rank0=stats.sent_bytes, recv_bytes_rank0=stats.recv_bytes,
                                     keys_owned_rank0=stats.n_out)
