@@ -7,7 +7,7 @@ GENCODE := -gencode arch=compute_100a,code=sm_100a
 NVFLAGS := -O3 -std=c++17 -lineinfo $(GENCODE) -Xcompiler -fPIC -Xcompiler -fvisibility=hidden --expt-relaxed-constexpr
 CSRC    := lsdradixsort_b200/csrc
 OBJDIR  := build/obj
-SRCS    := api.cu sort.cu histogram.cu scan.cu onesweep_r1.cu onesweep_r2.cu onesweep_r4.cu onesweep_r8.cu onesweep_r8_a.cu onesweep_r8_b.cu onesweep_r8_c.cu onesweep_r8_d.cu
+SRCS    := api.cu multi.cu sort.cu histogram.cu scan.cu onesweep_r1.cu onesweep_r2.cu onesweep_r4.cu onesweep_r8.cu onesweep_r8_a.cu onesweep_r8_b.cu onesweep_r8_c.cu onesweep_r8_d.cu
 OBJS    := $(addprefix $(OBJDIR)/,$(SRCS:.cu=.o))
 LIB     := lsdradixsort_b200/liblsdsort.so
 
@@ -24,7 +24,15 @@ $(LIB): $(OBJS)
 	$(NVCC) $(GENCODE) -shared -o $@ $(OBJS)
 
 # lsd_bench: the reference's Test*/Benchmark* drivers over the C ABI (tools/lsd_bench.cpp)
-tools: build/lsd_bench
+tools: build/lsd_bench build/lsd_multi_check
+# lsd_multi_check: lsd_sort_multi called from C++ threads with NCCL communicators (tools/lsd_multi_check.cpp); skipped
+# without nccl.h
+build/lsd_multi_check: tools/lsd_multi_check.cpp include/lsdsort.h include/lsdsort_nccl.h $(LIB)
+	@mkdir -p build
+	@if [ -f /usr/include/nccl.h ]; then \
+	  $(CXX) -O2 -std=c++17 -pthread -Iinclude -I$(CUDA_HOME)/include -o $@ $< -Llsdradixsort_b200 -llsdsort \
+	    -L$(CUDA_HOME)/lib64 -lcudart -lnccl -Wl,-rpath,'$$ORIGIN/../lsdradixsort_b200' ; \
+	else echo "nccl.h not found: skipping lsd_multi_check"; fi
 build/lsd_bench: tools/lsd_bench.cpp include/lsdsort.h $(LIB)
 	@mkdir -p build
 	$(CXX) -O2 -std=c++17 -Iinclude -I$(CUDA_HOME)/include -o $@ $< -Llsdradixsort_b200 -llsdsort \

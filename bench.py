@@ -381,11 +381,17 @@ def run_ours(args):
 
     if distributed:
         capacity = int(n_local * 1.25) + (1 << 16)
-        ops = multi.CudaOps(capacity, r=R_BITS, block=args.block)
         recv = torch.empty(capacity, dtype=torch.int32, device=dev)
-        staging = torch.empty(n_local, dtype=torch.int32, device=dev)
-        sorter = ops.sorter
-        peer = multi.PeerExchange(recv) if args.exchange == "peer" else None
+        sorter = L.Sorter(n_local, r=R_BITS, block=args.block)  # roofline leg: per-kernel times of a local sort
+        if args.exchange == "peer":
+            # the product path: ONE call of the C ABI's lsd_sort_multi per step (csrc/multi.cu); torch.distributed only
+            # supplies its two collectives (a 2 KiB all-gather, a barrier) as callbacks
+            peer = multi.MultiSorter(recv, r=R_BITS)
+            ops = staging = None
+        else:
+            peer = None
+            ops = multi.CudaOps(capacity, r=R_BITS, block=args.block)
+            staging = torch.empty(n_local, dtype=torch.int32, device=dev)
 
         def step():
             return multi.distributed_sort(work, ops, recv, staging, peer=peer)
@@ -491,8 +497,9 @@ def run_ours(args):
     }
     launches_per_sort = sorter.info(n_roof).launches
     per_step = launches_per_sort
-    if distributed:  # + top-digit histogram + partition pass (histogram unless fused, plan, one launch per portion)
-        per_step += 1 + (1 if peer is not None else 2) + max(1, (launches_per_sort - 3) // 4)
+    if distributed:  # local sort of the received keys (same launch count per key range) + top-digit histogram + multi plan
+        per_step = sorter.info(n_roof).launches  # + partition pass (plan + one launch per portion; + histogram on the NCCL path)
+        per_step += 2 + (1 if peer is not None else 2) + max(1, (launches_per_sort - 3) // 4)
     gpu_launches = args.steps * per_step
 
     # ---- exchange leg (N > 1): per-stage device times of one more step, NVLink roofline of the exchange ----
@@ -506,8 +513,8 @@ def run_ours(args):
         xt = torch.tensor([sm["partition"] + sm["all_to_all"], float(st_x.sent_bytes)], dtype=torch.float64, device=dev)
         dist.all_reduce(xt, op=dist.ReduceOp.MAX)
         x_ms, x_bytes = float(xt[0].item()), float(xt[1].item())
-        exchange = {"mode": "fused partition+exchange: the top-digit pass kernel stores each rank's keys into the owner's "
-                            "buffer over NVLink peer memory (CUDA IPC), no all-to-all" if peer is not None
+        exchange = {"mode": "lsd_sort_multi (C ABI): plan on the device, then the top-digit pass kernel stores each rank's keys "
+                            "into the owner's buffer over NVLink peer memory (CUDA IPC), no all-to-all" if peer is not None
                     else "stable top-digit partition pass + NCCL all_to_all_single",
                     "stages_ms_rank0": {k: round(v, 3) for k, v in sm.items()},
                     "partition_plus_exchange_ms_max": round(x_ms, 3), "sent_bytes_per_gpu_max": int(x_bytes),

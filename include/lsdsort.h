@@ -47,7 +47,9 @@ enum lsd_status {
     LSD_ERR_WORKSPACE_TOO_SMALL = 2, /* ws_bytes < the matching *_workspace_bytes query */
     LSD_ERR_CUDA = 3,                /* a CUDA call or launch failed; see lsd_last_cuda_error */
     LSD_ERR_UNSUPPORTED = 4,         /* size beyond what this build addresses, or a tuning variant without the requested form */
-    LSD_ERR_ALIGNMENT = 5            /* key pointers must be 16-byte aligned, workspace 256-byte */
+    LSD_ERR_ALIGNMENT = 5,           /* key pointers must be 16-byte aligned, workspace 256-byte */
+    LSD_ERR_CAPACITY = 6,            /* lsd_sort_multi: some rank would own more keys than its receive buffer holds */
+    LSD_ERR_COMM = 7                 /* lsd_sort_multi: a communication callback reported failure */
 };
 
 #define LSD_VERSION 100 /* 0.1.0 */
@@ -177,6 +179,61 @@ LSD_API int lsd_sort_pass_scatter(const uint32_t *in, uint64_t n, int r, int bit
 LSD_API int lsd_ipc_export(const void *dev_ptr, void *handle64, uint64_t *offset_out);
 LSD_API int lsd_ipc_open(const void *handle64, uint64_t offset, void **peer_ptr_out);
 LSD_API int lsd_ipc_close(void *peer_ptr, uint64_t offset);
+
+/* ---------------------------------------------------------------------------------------
+ * Multi-GPU sort (one process or thread per GPU, one node).  No reference counterpart: the reference is single-GPU
+ * (SURVEY 2.4); this is BASELINE.json's partitioning: every rank histograms the top 8-bit digit of its
+ * keys, the 256-bin rows are all-gathered (their sum is the all-reduced MSD histogram), every rank derives the same
+ * contiguous bucket -> rank map ON THE DEVICE, one pass kernel partitions the local keys by owner and stores them
+ * straight into the owners' receive buffers over NVLink peer memory (CUDA IPC; lsd_sort_pass_scatter), and every rank
+ * sorts what arrived.  Rank k ends with the k-th slice of the global order in its receive buffer.
+ *
+ * The two collectives are callbacks, so liblsdsort links no communication library: include/lsdsort_nccl.h fills an
+ * lsd_multi_comm from an ncclComm_t, lsdradixsort_b200/multi.py from torch.distributed.  Both must be ordered on the
+ * stream they are given (as NCCL calls are) and return 0 on success.
+ * ------------------------------------------------------------------------------------- */
+typedef struct lsd_multi_comm {
+    uint32_t struct_bytes; /* sizeof(lsd_multi_comm) */
+    int rank, nranks;      /* nranks <= 64 */
+    /* gather `bytes` bytes from every rank's DEVICE buffer `send` into the DEVICE buffer `recv` (rank-major) */
+    int (*all_gather)(void *ctx, const void *send, void *recv, size_t bytes, lsd_stream_t stream);
+    /* work enqueued on `stream` after the barrier starts on no rank before every rank's work before it has finished */
+    int (*barrier)(void *ctx, lsd_stream_t stream);
+    void *ctx;
+} lsd_multi_comm;
+
+typedef struct lsd_multi_stats {
+    uint64_t n_in, n_out;   /* keys this rank brought / owns after the exchange */
+    uint64_t n_out_max;     /* the largest share of any rank */
+    uint64_t sent_bytes;    /* bytes that left this GPU over NVLink (excludes what it kept) */
+    uint32_t first_bucket;  /* top-digit buckets this rank owns: [first, last]; first > last when it owns none */
+    uint32_t last_bucket;
+    float plan_ms;          /* with lsd_multi_set_timing(ctx, 1): device time of histogram + all-gather + plan, */
+    float exchange_ms;      /* of barrier + partition/exchange pass + barrier, */
+    float sort_ms;          /* and of the local sort; 0 otherwise */
+    uint32_t reserved;
+} lsd_multi_stats;
+
+typedef struct lsd_multi_ctx lsd_multi_ctx;
+/* COLLECTIVE: every rank calls it with its own receive buffer (`capacity` keys, from cudaMalloc: it is exported with
+ * CUDA IPC and mapped by every other rank).  The context owns a small plan area and the local sort's workspace for
+ * `capacity` keys (lsd_sort_workspace_bytes), a side stream and 64 pinned bytes.  r must be 8. */
+LSD_API int lsd_multi_ctx_create(const lsd_multi_comm *comm, uint32_t *recv, uint64_t capacity, int r, lsd_multi_ctx **out,
+                                 lsd_stream_t stream);
+LSD_API int lsd_multi_ctx_destroy(lsd_multi_ctx *ctx);
+/* COLLECTIVE: sorts the union of every rank's `keys` (n_local keys each, not modified).  On return the rank's slice
+ * (*n_out keys, ascending; every key of rank k <= every key of rank k+1) is being written to the context's receive
+ * buffer on `stream`; `scratch` (capacity keys) is ping-pong space for the local sort.  No host synchronisation sits
+ * in front of the exchange; the call waits only for a 64-byte copy of the plan's result that overlaps the exchange pass
+ * (the host needs *n_out to enqueue the local sort).  If any rank's share exceeds its capacity (a skewed top digit: the
+ * balance is only as fine as one of the 256 buckets), EVERY rank returns LSD_ERR_CAPACITY, *n_out = the largest share
+ * (so the caller can retry with bigger buffers) and no key is moved. */
+LSD_API int lsd_sort_multi(lsd_multi_ctx *ctx, const uint32_t *keys, uint64_t n_local, uint32_t *scratch, uint64_t *n_out,
+                           lsd_stream_t stream);
+/* Stats of the most recent lsd_sort_multi on this context.  With timing enabled the call synchronises the stream of
+ * that sort first (CUDA events bracket its three stages). */
+LSD_API int lsd_multi_last_stats(lsd_multi_ctx *ctx, lsd_multi_stats *out);
+LSD_API int lsd_multi_set_timing(lsd_multi_ctx *ctx, int enabled);
 
 /* Same as lsd_sort_ex, but brackets every kernel with CUDA events on `stream`, synchronises,
  * and reports per-stage device times.  stage_ms[0] = digit histogram + plan, stage_ms[1+p] =

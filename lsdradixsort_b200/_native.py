@@ -21,6 +21,8 @@ LSD_ERR_WORKSPACE_TOO_SMALL = 2
 LSD_ERR_CUDA = 3
 LSD_ERR_UNSUPPORTED = 4
 LSD_ERR_ALIGNMENT = 5
+LSD_ERR_CAPACITY = 6
+LSD_ERR_COMM = 7
 LSD_KEY_U32, LSD_KEY_I32, LSD_KEY_F32 = 0, 1, 2
 
 
@@ -38,6 +40,37 @@ class SortOptions(C.Structure):
         ("variant", C.c_uint32),
         ("debug_trace", C.c_uint64),
         ("key_type", C.c_uint32),
+        ("reserved", C.c_uint32),
+    ]
+
+
+ALL_GATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p)
+BARRIER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p)
+
+
+class MultiComm(C.Structure):
+    """lsd_multi_comm: rank layout + the two collectives lsd_sort_multi needs, as callbacks."""
+    _fields_ = [
+        ("struct_bytes", C.c_uint32),
+        ("rank", C.c_int),
+        ("nranks", C.c_int),
+        ("all_gather", ALL_GATHER_FN),
+        ("barrier", BARRIER_FN),
+        ("ctx", C.c_void_p),
+    ]
+
+
+class MultiStats(C.Structure):
+    _fields_ = [
+        ("n_in", C.c_uint64),
+        ("n_out", C.c_uint64),
+        ("n_out_max", C.c_uint64),
+        ("sent_bytes", C.c_uint64),
+        ("first_bucket", C.c_uint32),
+        ("last_bucket", C.c_uint32),
+        ("plan_ms", C.c_float),
+        ("exchange_ms", C.c_float),
+        ("sort_ms", C.c_float),
         ("reserved", C.c_uint32),
     ]
 
@@ -99,6 +132,11 @@ def lib() -> C.CDLL:
         "lsd_ipc_export": (C.c_int, [vp, vp, u64p]),
         "lsd_ipc_open": (C.c_int, [vp, C.c_uint64, C.POINTER(vp)]),
         "lsd_ipc_close": (C.c_int, [vp, C.c_uint64]),
+        "lsd_multi_ctx_create": (C.c_int, [C.POINTER(MultiComm), vp, C.c_uint64, C.c_int, C.POINTER(vp), vp]),
+        "lsd_multi_ctx_destroy": (C.c_int, [vp]),
+        "lsd_sort_multi": (C.c_int, [vp, vp, C.c_uint64, vp, u64p, vp]),
+        "lsd_multi_last_stats": (C.c_int, [vp, C.POINTER(MultiStats)]),
+        "lsd_multi_set_timing": (C.c_int, [vp, C.c_int]),
         "lsd_sort_timed": (
             C.c_int,
             [vp, vp, C.c_uint64, C.c_int, C.c_int, vp, C.c_size_t, C.POINTER(SortOptions), vp,

@@ -56,6 +56,8 @@ LSD_API const char* lsd_status_string(int status)
         case LSD_ERR_CUDA: return "CUDA error";
         case LSD_ERR_UNSUPPORTED: return "unsupported size";
         case LSD_ERR_ALIGNMENT: return "misaligned pointer";
+        case LSD_ERR_CAPACITY: return "receive buffer too small for this rank's share";
+        case LSD_ERR_COMM: return "communication callback failed";
     }
     return "unknown status";
 }

@@ -1,0 +1,349 @@
+// multi.cu -- lsd_sort_multi: the multi-GPU sort behind the C ABI (one process or thread per GPU, one node).
+//
+// No reference counterpart: the reference is single-GPU.  This is BASELINE.json's partitioning
+// (SURVEY 8(e)): top-digit histogram per rank -> the rows are all-gathered (their sum is the all-reduced MSD histogram)
+// -> every rank derives the same contiguous bucket -> rank map -> one pass kernel partitions the local keys by
+// destination and stores them straight into the owners' receive buffers over NVLink peer memory (CUDA IPC) -> local
+// LSD sort of what arrived.  Everything between the histogram and the exchange is planned ON THE DEVICE
+// (multi_plan_kernel): no host round trip sits in front of the exchange.  The host only learns how many keys it owns
+// (needed to enqueue the local sort) from a 64-byte copy on a side stream that overlaps the exchange pass.
+//
+// The two collectives (a 2 KiB all-gather and a barrier) come from the caller as callbacks, so liblsdsort has no link
+// dependency on a communication library; include/lsdsort_nccl.h supplies them for an ncclComm_t, lsdradixsort_b200/
+// multi.py for torch.distributed.
+#include <new>
+#include <vector>
+
+#include <cstring>
+#include <unistd.h>
+
+#include "sort.h"
+
+namespace lsd {
+
+constexpr int kMultiBuckets = 256;  // the exchange partitions on the top 8-bit digit
+constexpr int kMultiMaxRanks = 64;
+
+struct MultiResult {              // written by multi_plan_kernel, copied to the host
+    uint64_t n_out;               // keys this rank owns after the exchange
+    uint64_t n_out_max;           // the largest share of any rank
+    uint64_t sent;                // keys this rank sends to other ranks
+    uint32_t overflow;            // some rank's share exceeds the capacity: nothing is moved
+    uint32_t first_bucket;        // this rank's bucket range [first, last]; first > last when it owns nothing
+    uint32_t last_bucket;
+    uint32_t pad[7];
+};
+static_assert(sizeof(MultiResult) == 64, "copied as 64 bytes");
+
+// One CTA of 256 threads (one per bucket).  per_rank: [nranks][256] top-digit counts (the all-gathered rows).
+// bucket b goes to rank floor(nranks * (keys before b + half of b) / total), made monotone: every rank owns a contiguous
+// run of buckets whose total is as close to total / nranks as whole buckets allow (the same rule as multi.assign_buckets).
+__global__ void __launch_bounds__(kMultiBuckets)
+multi_plan_kernel(const uint64_t* __restrict__ per_rank, int nranks, int rank, const uint64_t* __restrict__ peer_ptrs,
+                  uint64_t capacity, uint64_t* __restrict__ dst_ptrs, uint32_t* __restrict__ dst_seg,
+                  uint32_t* __restrict__ abort_flag, MultiResult* __restrict__ result)
+{
+    __shared__ uint64_t s_tot[kMultiBuckets];
+    __shared__ uint64_t s_scan[kMultiBuckets];
+    __shared__ int s_owner[kMultiBuckets];
+    __shared__ uint64_t s_share[kMultiMaxRanks];   // keys owned by rank d
+    __shared__ uint64_t s_before[kMultiMaxRanks];  // keys that sources ahead of me put into d's buffer
+    __shared__ uint64_t s_mine[kMultiMaxRanks];    // keys I send to d
+    __shared__ uint32_t s_first[kMultiMaxRanks], s_last[kMultiMaxRanks];
+    const int b = threadIdx.x;
+    uint64_t tot = 0;
+    for (int s = 0; s < nranks; ++s) tot += per_rank[(size_t)s * kMultiBuckets + b];
+    s_tot[b] = tot;
+    s_scan[b] = tot;
+    if (b < kMultiMaxRanks) {
+        s_share[b] = 0;
+        s_before[b] = 0;
+        s_mine[b] = 0;
+        s_first[b] = kMultiBuckets;
+        s_last[b] = 0;
+    }
+    __syncthreads();
+    for (int o = 1; o < kMultiBuckets; o <<= 1) {  // inclusive scan of the global histogram
+        const uint64_t t = b >= o ? s_scan[b - o] : 0;
+        __syncthreads();
+        s_scan[b] += t;
+        __syncthreads();
+    }
+    const uint64_t grand = s_scan[kMultiBuckets - 1];
+    int owner;
+    if (grand == 0) {
+        owner = b * nranks / kMultiBuckets;
+    } else {
+        const uint64_t twice_mid = 2 * (s_scan[b] - tot) + tot;  // < 2^41: the product below fits 64 bits for nranks <= 64
+        const uint64_t o = twice_mid * (uint64_t)nranks / (2 * grand);
+        owner = (int)(o < (uint64_t)(nranks - 1) ? o : (uint64_t)(nranks - 1));
+    }
+    s_owner[b] = owner;
+    __syncthreads();
+    // monotone even with empty buckets: running maximum
+    for (int o = 1; o < kMultiBuckets; o <<= 1) {
+        const int t = b >= o ? s_owner[b - o] : 0;
+        __syncthreads();
+        if (t > s_owner[b]) s_owner[b] = t;
+        __syncthreads();
+    }
+    owner = s_owner[b];
+    // per destination: total share, what the sources ahead of me send, what I send, its bucket range
+    atomicAdd(reinterpret_cast<unsigned long long*>(&s_share[owner]), (unsigned long long)tot);
+    uint64_t ahead = 0;
+    for (int s = 0; s < rank; ++s) ahead += per_rank[(size_t)s * kMultiBuckets + b];
+    atomicAdd(reinterpret_cast<unsigned long long*>(&s_before[owner]), (unsigned long long)ahead);
+    atomicAdd(reinterpret_cast<unsigned long long*>(&s_mine[owner]), (unsigned long long)per_rank[(size_t)rank * kMultiBuckets + b]);
+    atomicMin(&s_first[owner], (uint32_t)b);
+    atomicMax(&s_last[owner], (uint32_t)b);
+    __syncthreads();
+    // all buckets owned by one rank form ONE destination segment: the pass kernel appends the segment's keys of a tile
+    // as one block to the owner's buffer, where the block of source `rank` starts behind the blocks of the ranks ahead
+    dst_ptrs[b] = peer_ptrs[owner] + 4ull * s_before[owner];
+    dst_seg[b] = s_first[owner] | (s_last[owner] << 16);
+    if (b == 0) {
+        uint64_t mx = 0, sent = 0;
+        for (int d = 0; d < nranks; ++d) {
+            mx = s_share[d] > mx ? s_share[d] : mx;
+            if (d != rank) sent += s_mine[d];
+        }
+        result->n_out = s_share[rank];
+        result->n_out_max = mx;
+        result->sent = sent;
+        result->overflow = mx > capacity ? 1u : 0u;
+        result->first_bucket = s_first[rank];
+        result->last_bucket = s_last[rank];
+        *abort_flag = mx > capacity ? 1u : 0u;
+    }
+}
+
+}  // namespace lsd
+
+using namespace lsd;
+
+struct lsd_multi_ctx {
+    lsd_multi_comm comm;
+    int device = 0;
+    int r = 8;
+    uint32_t* recv = nullptr;
+    uint64_t capacity = 0;
+    std::vector<uint64_t> peer_ptrs;   // every rank's receive buffer as seen from this process
+    std::vector<uint64_t> peer_offs;   // offset of the buffer inside its IPC allocation (for lsd_ipc_close)
+    std::vector<char> peer_ipc;        // 1: mapped with lsd_ipc_open (another process)
+    // device workspace owned by the context
+    char* ws = nullptr;
+    size_t ws_bytes = 0;
+    size_t off_hist = 0, off_gather = 0, off_peers = 0, off_dst = 0, off_seg = 0, off_abort = 0, off_result = 0, off_sort = 0;
+    size_t sort_ws_bytes = 0;
+    MultiResult* host_result = nullptr;  // pinned
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_plan = nullptr, ev_copied = nullptr;
+    cudaEvent_t ev_t[4] = {nullptr, nullptr, nullptr, nullptr};  // stage boundaries when timing is on
+    bool timing = false, timed = false;
+    lsd_multi_stats last = {};
+};
+
+static size_t align256(size_t v) { return (v + 255) / 256 * 256; }
+
+extern "C" {
+
+LSD_API int lsd_multi_ctx_create(const lsd_multi_comm* comm, uint32_t* recv, uint64_t capacity, int r, lsd_multi_ctx** out,
+                                 lsd_stream_t stream)
+{
+    if (!comm || !out || !recv || capacity == 0) return LSD_ERR_INVALID_VALUE;
+    if (comm->struct_bytes != sizeof(lsd_multi_comm) || !comm->all_gather || !comm->barrier) return LSD_ERR_INVALID_VALUE;
+    if (comm->nranks < 1 || comm->nranks > kMultiMaxRanks || comm->rank < 0 || comm->rank >= comm->nranks) return LSD_ERR_INVALID_VALUE;
+    if (r != 8) return LSD_ERR_UNSUPPORTED;  // the exchange partitions on the top 8-bit digit
+    if (!aligned_to(recv, 16)) return LSD_ERR_ALIGNMENT;
+    lsd_multi_ctx* c = new (std::nothrow) lsd_multi_ctx();
+    if (!c) return LSD_ERR_INVALID_VALUE;
+    c->comm = *comm;
+    c->r = r;
+    c->recv = recv;
+    c->capacity = capacity;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int N = comm->nranks;
+    int rc = LSD_OK;
+    auto fail = [&](int code) {
+        lsd_multi_ctx_destroy(c);
+        return code;
+    };
+    if (cudaGetDevice(&c->device) != cudaSuccess) return fail(LSD_ERR_CUDA);
+    c->sort_ws_bytes = lsd_sort_workspace_bytes(capacity, r, 0);
+    size_t off = 0;
+    c->off_hist = off;    off = align256(off + sizeof(uint64_t) * (32 / r) * kMultiBuckets);
+    c->off_gather = off;  off = align256(off + sizeof(uint64_t) * (size_t)N * kMultiBuckets);
+    c->off_peers = off;   off = align256(off + sizeof(uint64_t) * N);
+    c->off_dst = off;     off = align256(off + sizeof(uint64_t) * kMultiBuckets);
+    c->off_seg = off;     off = align256(off + sizeof(uint32_t) * kMultiBuckets);
+    c->off_abort = off;   off = align256(off + 256);
+    c->off_result = off;  off = align256(off + sizeof(MultiResult));
+    c->off_sort = off;    off = align256(off + c->sort_ws_bytes);
+    c->ws_bytes = off;
+    if (cudaMalloc(&c->ws, c->ws_bytes) != cudaSuccess) return fail(LSD_ERR_CUDA);
+    if (cudaMallocHost(&c->host_result, sizeof(MultiResult)) != cudaSuccess) return fail(LSD_ERR_CUDA);
+    if (cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking) != cudaSuccess) return fail(LSD_ERR_CUDA);
+    if (cudaEventCreateWithFlags(&c->ev_plan, cudaEventDisableTiming) != cudaSuccess) return fail(LSD_ERR_CUDA);
+    if (cudaEventCreateWithFlags(&c->ev_copied, cudaEventDisableTiming) != cudaSuccess) return fail(LSD_ERR_CUDA);
+
+    // exchange the receive buffers' addresses through the all-gather callback (96 bytes per rank, staged in the gather
+    // area, which holds 2 KiB per rank): a CUDA IPC handle for ranks in other processes, the plain pointer (plus peer
+    // access) for ranks that are threads of this process
+    struct Handle { unsigned char h[64]; uint64_t off; uint64_t raw; int64_t pid; int32_t device; int32_t pad; };
+    static_assert(sizeof(Handle) == 96, "96 bytes per rank");
+    Handle mine;
+    memset(&mine, 0, sizeof(mine));
+    rc = lsd_ipc_export(recv, mine.h, &mine.off);
+    if (rc != LSD_OK) return fail(rc);
+    mine.raw = (uint64_t)(uintptr_t)recv;
+    mine.pid = (int64_t)getpid();
+    mine.device = c->device;
+    char* stage_send = c->ws + c->off_hist;
+    char* stage_recv = c->ws + c->off_gather;
+    if (cudaMemcpyAsync(stage_send, &mine, sizeof(mine), cudaMemcpyHostToDevice, s) != cudaSuccess) return fail(LSD_ERR_CUDA);
+    if (comm->all_gather(comm->ctx, stage_send, stage_recv, sizeof(Handle), stream) != 0) return fail(LSD_ERR_COMM);
+    std::vector<Handle> all(N);
+    if (cudaMemcpyAsync(all.data(), stage_recv, sizeof(Handle) * N, cudaMemcpyDeviceToHost, s) != cudaSuccess) return fail(LSD_ERR_CUDA);
+    if (cudaStreamSynchronize(s) != cudaSuccess) return fail(LSD_ERR_CUDA);
+    c->peer_ptrs.assign(N, 0);
+    c->peer_offs.assign(N, 0);
+    c->peer_ipc.assign(N, 0);
+    for (int p = 0; p < N; ++p) {
+        if (p == comm->rank) {
+            c->peer_ptrs[p] = (uint64_t)(uintptr_t)recv;
+        } else if (all[p].pid == mine.pid) {  // a thread of this process: the pointer is valid here, enable peer access
+            if (all[p].device != c->device) {
+                const cudaError_t e = cudaDeviceEnablePeerAccess(all[p].device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) {
+                    set_last_cuda_error(e);
+                    return fail(LSD_ERR_CUDA);
+                }
+                (void)cudaGetLastError();
+            }
+            c->peer_ptrs[p] = all[p].raw;
+        } else {
+            void* ptr = nullptr;
+            rc = lsd_ipc_open(all[p].h, all[p].off, &ptr);
+            if (rc != LSD_OK) return fail(rc);
+            c->peer_ptrs[p] = (uint64_t)(uintptr_t)ptr;
+            c->peer_offs[p] = all[p].off;
+            c->peer_ipc[p] = 1;
+        }
+    }
+    if (cudaMemcpyAsync(c->ws + c->off_peers, c->peer_ptrs.data(), sizeof(uint64_t) * N, cudaMemcpyHostToDevice, s) != cudaSuccess)
+        return fail(LSD_ERR_CUDA);
+    if (cudaStreamSynchronize(s) != cudaSuccess) return fail(LSD_ERR_CUDA);
+    if (comm->barrier(comm->ctx, stream) != 0) return fail(LSD_ERR_COMM);  // every rank has mapped every buffer
+    *out = c;
+    return LSD_OK;
+}
+
+LSD_API int lsd_multi_ctx_destroy(lsd_multi_ctx* c)
+{
+    if (!c) return LSD_OK;
+    for (size_t p = 0; p < c->peer_ptrs.size(); ++p)
+        if (p < c->peer_ipc.size() && c->peer_ipc[p]) lsd_ipc_close((void*)(uintptr_t)c->peer_ptrs[p], c->peer_offs[p]);
+    if (c->ev_plan) cudaEventDestroy(c->ev_plan);
+    if (c->ev_copied) cudaEventDestroy(c->ev_copied);
+    for (cudaEvent_t e : c->ev_t)
+        if (e) cudaEventDestroy(e);
+    if (c->side) cudaStreamDestroy(c->side);
+    if (c->host_result) cudaFreeHost(c->host_result);
+    if (c->ws) cudaFree(c->ws);
+    delete c;
+    return LSD_OK;
+}
+
+LSD_API int lsd_sort_multi(lsd_multi_ctx* c, const uint32_t* keys, uint64_t n_local, uint32_t* scratch, uint64_t* n_out,
+                           lsd_stream_t stream)
+{
+    if (!c || !n_out || (n_local > 0 && !keys) || !scratch) return LSD_ERR_INVALID_VALUE;
+    if (n_local > 0 && !aligned_to(keys, 16)) return LSD_ERR_ALIGNMENT;
+    if (!aligned_to(scratch, 16)) return LSD_ERR_ALIGNMENT;
+    cudaStream_t s = (cudaStream_t)stream;
+    const lsd_multi_comm& comm = c->comm;
+    const int N = comm.nranks;
+    uint64_t* hist = reinterpret_cast<uint64_t*>(c->ws + c->off_hist);
+    uint64_t* gathered = reinterpret_cast<uint64_t*>(c->ws + c->off_gather);
+    const uint64_t* peers = reinterpret_cast<const uint64_t*>(c->ws + c->off_peers);
+    uint64_t* dst = reinterpret_cast<uint64_t*>(c->ws + c->off_dst);
+    uint32_t* seg = reinterpret_cast<uint32_t*>(c->ws + c->off_seg);
+    uint32_t* abort_flag = reinterpret_cast<uint32_t*>(c->ws + c->off_abort);
+    MultiResult* result = reinterpret_cast<MultiResult*>(c->ws + c->off_result);
+    void* sort_ws = c->ws + c->off_sort;
+    const int top = 32 / c->r - 1;
+
+    c->timed = false;
+    if (c->timing) LSD_CUDA_TRY(cudaEventRecord(c->ev_t[0], s));
+    // 1. top-digit histogram of the local keys: row `top` of the [32/r][256] layout
+    int rc = lsd_top_digit_histogram(keys, n_local, c->r, hist, stream);
+    if (rc != LSD_OK) return rc;
+    // 2. the rows of all ranks (their sum is the all-reduced MSD histogram)
+    if (comm.all_gather(comm.ctx, hist + (size_t)top * kMultiBuckets, gathered, sizeof(uint64_t) * kMultiBuckets, stream) != 0)
+        return LSD_ERR_COMM;
+    // 3. bucket -> rank map, destination pointers and segments, shares: on the device
+    multi_plan_kernel<<<1, kMultiBuckets, 0, s>>>(gathered, N, comm.rank, peers, c->capacity, dst, seg, abort_flag, result);
+    LSD_LAUNCH_CHECK();
+    LSD_CUDA_TRY(cudaEventRecord(c->ev_plan, s));
+    LSD_CUDA_TRY(cudaStreamWaitEvent(c->side, c->ev_plan, 0));
+    LSD_CUDA_TRY(cudaMemcpyAsync(c->host_result, result, sizeof(MultiResult), cudaMemcpyDeviceToHost, c->side));
+    LSD_CUDA_TRY(cudaEventRecord(c->ev_copied, c->side));
+    if (c->timing) LSD_CUDA_TRY(cudaEventRecord(c->ev_t[1], s));
+    // 4. fused partition + exchange: every rank is done reading what the previous exchange left in its buffer, then the
+    //    pass stores each destination segment into its owner's buffer, then every rank's stores have landed.  The pass
+    //    is skipped on the device (abort_flag) when some rank's share exceeds its buffer.
+    if (comm.barrier(comm.ctx, stream) != 0) return LSD_ERR_COMM;
+    rc = pass_enqueue(keys, nullptr, n_local, c->r, top, 0, sort_ws, c->sort_ws_bytes, nullptr, s, dst, seg, abort_flag);
+    if (rc != LSD_OK) return rc;
+    if (comm.barrier(comm.ctx, stream) != 0) return LSD_ERR_COMM;
+    if (c->timing) LSD_CUDA_TRY(cudaEventRecord(c->ev_t[2], s));
+    // the host needs its share to enqueue the local sort: the 64-byte copy ran beside the exchange pass
+    LSD_CUDA_TRY(cudaEventSynchronize(c->ev_copied));
+    const MultiResult res = *c->host_result;
+    c->last.n_in = n_local;
+    c->last.n_out = res.n_out;
+    c->last.n_out_max = res.n_out_max;
+    c->last.sent_bytes = 4 * res.sent;
+    c->last.first_bucket = res.first_bucket;
+    c->last.last_bucket = res.last_bucket;
+    *n_out = res.n_out;
+    if (res.overflow) {  // identical on every rank: all return the same status, nothing was moved
+        *n_out = res.n_out_max;
+        return LSD_ERR_CAPACITY;
+    }
+    // 5. local LSD sort of the owned key range
+    rc = lsd_sort(c->recv, scratch, res.n_out, c->r, 0, sort_ws, c->sort_ws_bytes, stream);
+    if (rc != LSD_OK) return rc;
+    if (c->timing) {
+        LSD_CUDA_TRY(cudaEventRecord(c->ev_t[3], s));
+        c->timed = true;
+    }
+    return LSD_OK;
+}
+
+LSD_API int lsd_multi_last_stats(lsd_multi_ctx* c, lsd_multi_stats* out)
+{
+    if (!c || !out) return LSD_ERR_INVALID_VALUE;
+    c->last.plan_ms = c->last.exchange_ms = c->last.sort_ms = 0.f;
+    if (c->timed) {
+        LSD_CUDA_TRY(cudaEventSynchronize(c->ev_t[3]));
+        LSD_CUDA_TRY(cudaEventElapsedTime(&c->last.plan_ms, c->ev_t[0], c->ev_t[1]));
+        LSD_CUDA_TRY(cudaEventElapsedTime(&c->last.exchange_ms, c->ev_t[1], c->ev_t[2]));
+        LSD_CUDA_TRY(cudaEventElapsedTime(&c->last.sort_ms, c->ev_t[2], c->ev_t[3]));
+    }
+    *out = c->last;
+    return LSD_OK;
+}
+
+LSD_API int lsd_multi_set_timing(lsd_multi_ctx* c, int enabled)
+{
+    if (!c) return LSD_ERR_INVALID_VALUE;
+    if (enabled)
+        for (cudaEvent_t& e : c->ev_t)
+            if (!e) LSD_CUDA_TRY(cudaEventCreate(&e));
+    c->timing = enabled != 0;
+    c->timed = false;
+    return LSD_OK;
+}
+
+}  // extern "C"

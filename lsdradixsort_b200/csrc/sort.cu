@@ -255,7 +255,7 @@ int sort_enqueue(uint32_t* keys, uint32_t* scratch, uint64_t n, int r, int block
 // -------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kPlanThreads)
 single_pass_plan_kernel(const uint64_t* __restrict__ hist, uint64_t* __restrict__ bases, SortPlan* __restrict__ plan,
-                        uint64_t* __restrict__ hist_out, int pass, int H, int zero_bases)
+                        uint64_t* __restrict__ hist_out, int pass, int H, int zero_bases, const uint32_t* __restrict__ abort_flag)
 {
     __shared__ uint64_t s_warp[kPlanThreads / 32];
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
@@ -276,13 +276,14 @@ single_pass_plan_kernel(const uint64_t* __restrict__ hist, uint64_t* __restrict_
         if (hist_out) hist_out[tid] = prefix + incl - v;
     }
     if (tid == 0) {
-        plan->skip[pass] = 0;
+        plan->skip[pass] = (abort_flag != nullptr && *abort_flag != 0u) ? 1u : 0u;
         plan->src_is_scratch[pass] = 0;  // PassArgs.keys = in, PassArgs.scratch = out
     }
 }
 
 int pass_enqueue(const uint32_t* in, uint32_t* out, uint64_t n, int r, int bit_group, int block, void* ws,
-                 size_t ws_bytes, uint64_t* hist_out, cudaStream_t s, const uint64_t* dst_ptrs, const uint32_t* dst_seg)
+                 size_t ws_bytes, uint64_t* hist_out, cudaStream_t s, const uint64_t* dst_ptrs, const uint32_t* dst_seg,
+                 const uint32_t* abort_flag)
 {
     SortLayout L;
     const int st = make_layout(n, r, block, nullptr, &L);
@@ -312,7 +313,7 @@ int pass_enqueue(const uint32_t* in, uint32_t* out, uint64_t n, int r, int bit_g
         rc = launch_digit_histograms(in, n, r, hist, s);
         if (rc != LSD_OK) return rc;
     }
-    single_pass_plan_kernel<<<1, kPlanThreads, 0, s>>>(hist, bases, plan, peer ? nullptr : hist_out, bit_group, L.H, peer ? 1 : 0);
+    single_pass_plan_kernel<<<1, kPlanThreads, 0, s>>>(hist, bases, plan, peer ? nullptr : hist_out, bit_group, L.H, peer ? 1 : 0, abort_flag);
     LSD_LAUNCH_CHECK();
     uint32_t* lb = lookback;
     for (uint64_t q = 0; q < L.portions; ++q) {

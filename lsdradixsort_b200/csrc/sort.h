@@ -26,8 +26,9 @@ int sort_enqueue(uint32_t* keys, uint32_t* scratch, uint64_t n, int r, int block
 
 // One stable pass on `bit_group` from `in` to `out` (no plan, never skipped).  With dst_ptrs != nullptr the pass
 // runs in peer-scatter mode instead (see lsd_sort_pass_scatter in include/lsdsort.h); `out` and `hist_out` are unused.
+// abort_flag (device, optional): the pass exits at once if *abort_flag != 0 when its plan kernel runs.
 int pass_enqueue(const uint32_t* in, uint32_t* out, uint64_t n, int r, int bit_group, int block, void* ws,
                  size_t ws_bytes, uint64_t* hist_out, cudaStream_t s, const uint64_t* dst_ptrs = nullptr,
-                 const uint32_t* dst_seg = nullptr);
+                 const uint32_t* dst_seg = nullptr, const uint32_t* abort_flag = nullptr);
 
 }  // namespace lsd

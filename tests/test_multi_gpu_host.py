@@ -144,3 +144,38 @@ def test_distributed_sort_gloo(world, kind):
     got = np.concatenate([r[1] for r in results])  # rank order == global order
     assert np.array_equal(got, np.sort(whole))
     assert sum(r[2] for r in results) == whole.size
+
+
+def _worker_capacity(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        keys = torch.from_numpy(keygen.make_keys("all_equal", 4000, seed=1).view(np.int32).copy())
+        recv = torch.empty(5000, dtype=torch.int32)  # holds one rank's share of a uniform input, not all 8000 equal keys
+        staging = torch.empty(4000, dtype=torch.int32)
+        try:
+            multi.distributed_sort(keys, OracleOps(), recv, staging)
+            q.put((rank, None))
+        except multi.CapacityError as e:
+            q.put((rank, (e.needed, e.capacity)))
+        dist.barrier()  # every rank is still alive and in step: nobody is stuck in the exchange
+    finally:
+        dist.destroy_process_group()
+
+
+def test_distributed_sort_capacity_error_is_raised_on_every_rank():
+    """An all-equal input lands on one rank.  The rank that owns nothing must raise as well, or the owner's peers would
+    block in all_to_all_single (multi.py:188)."""
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_capacity, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = sorted((q.get(timeout=120) for _ in range(world)), key=lambda t: t[0])
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    assert [r[1] for r in results] == [(8000, 5000)] * world

@@ -1,0 +1,135 @@
+"""lsd_sort_multi on ONE GPU (-m gpu): the ranks are host threads of this process that share device 0, so the whole
+multi-GPU path of the C ABI -- device-side plan, peer-store exchange pass (the "peers" are buffers on the same device),
+local sort, capacity status -- runs in the single-GPU test tier.  The two collectives are thread-level test doubles
+(a host barrier after a stream synchronise; device-to-device copies); on real multi-GPU boxes
+tests/test_multi_gpu_device.py runs the same entry over NCCL."""
+import ctypes as C
+import threading
+
+import numpy as np
+import pytest
+import torch
+
+from lsdradixsort_b200 import _native as N
+from lsdradixsort_b200 import api, keygen, multi
+
+pytestmark = pytest.mark.gpu
+
+
+class _Raw:
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 3}
+
+
+def _as_bytes(ptr, nbytes):
+    return torch.as_tensor(_Raw(ptr, nbytes), device="cuda")
+
+
+class ThreadComm:
+    """all_gather / barrier for `world` threads that share one device."""
+
+    def __init__(self, world):
+        self.world = world
+        self.bar = threading.Barrier(world)
+        self.send = [None] * world
+
+    def callbacks(self, rank):
+        def all_gather(_ctx, send, recv, nbytes, _stream):
+            try:
+                torch.cuda.synchronize()
+                self.send[rank] = send
+                self.bar.wait()
+                for s in range(self.world):
+                    _as_bytes(recv + s * nbytes, nbytes).copy_(_as_bytes(self.send[s], nbytes))
+                torch.cuda.synchronize()
+                self.bar.wait()
+                return 0
+            except Exception:  # noqa: BLE001
+                return 1
+
+        def barrier(_ctx, _stream):
+            try:
+                torch.cuda.synchronize()
+                self.bar.wait()
+                return 0
+            except Exception:  # noqa: BLE001
+                return 1
+
+        return N.ALL_GATHER_FN(all_gather), N.BARRIER_FN(barrier)
+
+
+def _rank_main(rank, comm, keys_np, capacity, results, errors):
+    try:
+        lib = N.lib()
+        cb = comm.callbacks(rank)
+        mc = N.MultiComm(C.sizeof(N.MultiComm), rank, comm.world, cb[0], cb[1], None)
+        src = torch.from_numpy(keys_np.view(np.int32)).cuda()
+        recv = torch.full((capacity,), 0x5A5A5A5A, dtype=torch.int32, device="cuda")
+        scratch = torch.empty(capacity, dtype=torch.int32, device="cuda")
+        ctx = C.c_void_p()
+        st = lib.lsd_multi_ctx_create(C.byref(mc), recv.data_ptr(), capacity, 8, C.byref(ctx), api._stream_ptr(src.device))
+        assert st == N.LSD_OK, st
+        n_out = C.c_uint64(0)
+        st = lib.lsd_sort_multi(ctx, src.data_ptr(), src.numel(), scratch.data_ptr(), C.byref(n_out), api._stream_ptr(src.device))
+        torch.cuda.synchronize()
+        ms = N.MultiStats()
+        lib.lsd_multi_last_stats(ctx, C.byref(ms))
+        comm.bar.wait()  # nobody unmaps while a peer may still be writing
+        results[rank] = (st, int(n_out.value), recv[: int(n_out.value)].cpu().numpy().view(np.uint32).copy() if st == 0 else None,
+                         bool((recv == 0x5A5A5A5A).all()) if st != 0 else None, (int(ms.first_bucket), int(ms.last_bucket), int(ms.n_out_max)))
+        lib.lsd_multi_ctx_destroy(ctx)
+    except Exception as e:  # noqa: BLE001
+        errors.append((rank, repr(e)))
+        try:
+            comm.bar.abort()
+        except Exception:  # noqa: BLE001
+            pass
+
+
+def _run(world, kind, n_local, capacity):
+    comm = ThreadComm(world)
+    keys = [keygen.make_keys(kind, n_local, seed=900 + r) for r in range(world)]
+    results, errors = [None] * world, []
+    threads = [threading.Thread(target=_rank_main, args=(r, comm, keys[r], capacity, results, errors)) for r in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(300)
+    assert not errors, errors
+    return keys, results
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 4])
+@pytest.mark.parametrize("kind", ["uniform", "entropy4_table", "sorted", "all_equal"])
+def test_sort_multi_threads_on_one_gpu(world, kind):
+    n_local = 200_000 + 17 * world
+    keys, results = _run(world, kind, n_local, capacity=n_local * world + 64)
+    assert all(r[0] == N.LSD_OK for r in results)
+    whole = np.sort(np.concatenate(keys))
+    assert np.array_equal(np.concatenate([r[2] for r in results]), whole)  # rank order == global order
+    assert sum(r[1] for r in results) == whole.size
+    # the device-side plan is the same map the host-side numpy plan derives (multi.assign_buckets)
+    per_rank = np.stack([np.bincount(k >> np.uint32(24), minlength=256) for k in keys]).astype(np.int64)
+    owner = multi.assign_buckets(per_rank.sum(axis=0), world)
+    for r, res in enumerate(results):
+        mine = np.nonzero(owner == r)[0]
+        if mine.size:
+            assert res[4][0] == int(mine[0]) and res[4][1] == int(mine[-1])
+        else:
+            assert res[4][0] > res[4][1]
+        assert res[1] == int(per_rank[:, owner == r].sum())
+
+
+def test_sort_multi_capacity_status_on_every_rank_and_nothing_moves():
+    world, n_local = 3, 100_000
+    keys, results = _run(world, "all_equal", n_local, capacity=n_local + 64)  # one bucket: everything lands on one rank
+    assert [r[0] for r in results] == [N.LSD_ERR_CAPACITY] * world
+    assert all(r[1] == n_local * world for r in results)  # *n_out reports the largest share
+    assert all(r[3] for r in results)  # receive buffers untouched
+
+
+def test_sort_multi_larger_uniform_two_ranks():
+    world, n_local = 2, 1 << 23
+    keys, results = _run(world, "uniform", n_local, capacity=int(n_local * 1.25))
+    assert all(r[0] == N.LSD_OK for r in results)
+    assert np.array_equal(np.concatenate([r[2] for r in results]), np.sort(np.concatenate(keys)))
