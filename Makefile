@@ -7,9 +7,20 @@ GENCODE := -gencode arch=compute_100a,code=sm_100a
 NVFLAGS := -O3 -std=c++17 -lineinfo $(GENCODE) -Xcompiler -fPIC -Xcompiler -fvisibility=hidden --expt-relaxed-constexpr
 CSRC    := lsdradixsort_b200/csrc
 OBJDIR  := build/obj
-SRCS    := api.cu multi.cu sort.cu histogram.cu scan.cu onesweep_r1.cu onesweep_r2.cu onesweep_r4.cu onesweep_r8.cu onesweep_r8_a.cu onesweep_r8_b.cu onesweep_r8_c.cu onesweep_r8_d.cu
-OBJS    := $(addprefix $(OBJDIR)/,$(SRCS:.cu=.o))
+# TUNING=1 appends the measured-and-rejected kernel families (onesweep_r8_{b,c,d}.cu and the #ifdef'd table entries) as
+# lsd_sort_options.variant values: a separate library, lsdradixsort_b200/liblsdsort_tuning.so (use it with
+# LSDSORT_LIB=...; bench_tools/ and the variant tests need it).  The product library holds the shipped shapes only.
+TUNING  ?= 0
+SRCS    := api.cu multi.cu sort.cu histogram.cu scan.cu onesweep_r1.cu onesweep_r2.cu onesweep_r4.cu onesweep_r8.cu onesweep_r8_a.cu
+ifeq ($(TUNING),1)
+SRCS    += onesweep_r8_b.cu onesweep_r8_c.cu onesweep_r8_d.cu
+NVFLAGS += -DLSD_TUNING_VARIANTS
+OBJDIR  := build/obj_tuning
+LIB     := lsdradixsort_b200/liblsdsort_tuning.so
+else
 LIB     := lsdradixsort_b200/liblsdsort.so
+endif
+OBJS    := $(addprefix $(OBJDIR)/,$(SRCS:.cu=.o))
 
 .PHONY: all lib oracle tools clean
 all: lib oracle tools

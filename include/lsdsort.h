@@ -216,12 +216,13 @@ typedef struct lsd_multi_stats {
 
 typedef struct lsd_multi_ctx lsd_multi_ctx;
 /* COLLECTIVE: every rank calls it with its own receive buffer (`capacity` keys, from cudaMalloc: it is exported with
- * CUDA IPC and mapped by every other rank).  The context owns a small plan area and the local sort's workspace for
- * `capacity` keys (lsd_sort_workspace_bytes), a side stream and 64 pinned bytes.  r must be 8. */
-LSD_API int lsd_multi_ctx_create(const lsd_multi_comm *comm, uint32_t *recv, uint64_t capacity, int r, lsd_multi_ctx **out,
-                                 lsd_stream_t stream);
+ * CUDA IPC and mapped by every other rank).  max_n_local bounds the n_local of later lsd_sort_multi calls on this rank.
+ * The context owns a small plan area and one workspace for max(capacity, max_n_local) keys (lsd_sort_workspace_bytes;
+ * shared by the exchange pass and the local sort), a side stream and 64 pinned bytes.  r must be 8. */
+LSD_API int lsd_multi_ctx_create(const lsd_multi_comm *comm, uint32_t *recv, uint64_t capacity, uint64_t max_n_local, int r,
+                                 lsd_multi_ctx **out, lsd_stream_t stream);
 LSD_API int lsd_multi_ctx_destroy(lsd_multi_ctx *ctx);
-/* COLLECTIVE: sorts the union of every rank's `keys` (n_local keys each, not modified).  On return the rank's slice
+/* COLLECTIVE: sorts the union of every rank's `keys` (n_local <= max_n_local keys each, not modified).  On return the rank's slice
  * (*n_out keys, ascending; every key of rank k <= every key of rank k+1) is being written to the context's receive
  * buffer on `stream`; `scratch` (capacity keys) is ping-pong space for the local sort.  No host synchronisation sits
  * in front of the exchange; the call waits only for a 64-byte copy of the plan's result that overlaps the exchange pass

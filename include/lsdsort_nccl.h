@@ -7,7 +7,7 @@
  *     lsd_nccl_comm state;
  *     lsd_multi_comm comm;
  *     lsd_multi_comm_from_nccl(&state, nccl_comm, rank, nranks, token_dev, &comm);   // token_dev: one int of device memory
- *     lsd_multi_ctx_create(&comm, recv, capacity, 8, &ctx, stream);
+ *     lsd_multi_ctx_create(&comm, recv, capacity, n_local, 8, &ctx, stream);
  *     lsd_sort_multi(ctx, keys, n_local, scratch, &n_out, stream);
  */
 #ifndef LSDSORT_NCCL_H

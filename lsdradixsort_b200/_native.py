@@ -132,7 +132,7 @@ def lib() -> C.CDLL:
         "lsd_ipc_export": (C.c_int, [vp, vp, u64p]),
         "lsd_ipc_open": (C.c_int, [vp, C.c_uint64, C.POINTER(vp)]),
         "lsd_ipc_close": (C.c_int, [vp, C.c_uint64]),
-        "lsd_multi_ctx_create": (C.c_int, [C.POINTER(MultiComm), vp, C.c_uint64, C.c_int, C.POINTER(vp), vp]),
+        "lsd_multi_ctx_create": (C.c_int, [C.POINTER(MultiComm), vp, C.c_uint64, C.c_uint64, C.c_int, C.POINTER(vp), vp]),
         "lsd_multi_ctx_destroy": (C.c_int, [vp]),
         "lsd_sort_multi": (C.c_int, [vp, vp, C.c_uint64, vp, u64p, vp]),
         "lsd_multi_last_stats": (C.c_int, [vp, C.POINTER(MultiStats)]),

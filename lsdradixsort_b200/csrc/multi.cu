@@ -127,6 +127,7 @@ struct lsd_multi_ctx {
     int r = 8;
     uint32_t* recv = nullptr;
     uint64_t capacity = 0;
+    uint64_t max_n_local = 0;
     std::vector<uint64_t> peer_ptrs;   // every rank's receive buffer as seen from this process
     std::vector<uint64_t> peer_offs;   // offset of the buffer inside its IPC allocation (for lsd_ipc_close)
     std::vector<char> peer_ipc;        // 1: mapped with lsd_ipc_open (another process)
@@ -147,8 +148,8 @@ static size_t align256(size_t v) { return (v + 255) / 256 * 256; }
 
 extern "C" {
 
-LSD_API int lsd_multi_ctx_create(const lsd_multi_comm* comm, uint32_t* recv, uint64_t capacity, int r, lsd_multi_ctx** out,
-                                 lsd_stream_t stream)
+LSD_API int lsd_multi_ctx_create(const lsd_multi_comm* comm, uint32_t* recv, uint64_t capacity, uint64_t max_n_local, int r,
+                                 lsd_multi_ctx** out, lsd_stream_t stream)
 {
     if (!comm || !out || !recv || capacity == 0) return LSD_ERR_INVALID_VALUE;
     if (comm->struct_bytes != sizeof(lsd_multi_comm) || !comm->all_gather || !comm->barrier) return LSD_ERR_INVALID_VALUE;
@@ -169,7 +170,9 @@ LSD_API int lsd_multi_ctx_create(const lsd_multi_comm* comm, uint32_t* recv, uin
         return code;
     };
     if (cudaGetDevice(&c->device) != cudaSuccess) return fail(LSD_ERR_CUDA);
-    c->sort_ws_bytes = lsd_sort_workspace_bytes(capacity, r, 0);
+    c->max_n_local = max_n_local;
+    c->sort_ws_bytes = lsd_sort_workspace_bytes(capacity > max_n_local ? capacity : max_n_local, r, 0);
+    if (c->sort_ws_bytes == 0) return fail(LSD_ERR_UNSUPPORTED);
     size_t off = 0;
     c->off_hist = off;    off = align256(off + sizeof(uint64_t) * (32 / r) * kMultiBuckets);
     c->off_gather = off;  off = align256(off + sizeof(uint64_t) * (size_t)N * kMultiBuckets);
@@ -258,6 +261,7 @@ LSD_API int lsd_sort_multi(lsd_multi_ctx* c, const uint32_t* keys, uint64_t n_lo
                            lsd_stream_t stream)
 {
     if (!c || !n_out || (n_local > 0 && !keys) || !scratch) return LSD_ERR_INVALID_VALUE;
+    if (n_local > c->max_n_local) return LSD_ERR_INVALID_VALUE;
     if (n_local > 0 && !aligned_to(keys, 16)) return LSD_ERR_ALIGNMENT;
     if (!aligned_to(scratch, 16)) return LSD_ERR_ALIGNMENT;
     cudaStream_t s = (cudaStream_t)stream;

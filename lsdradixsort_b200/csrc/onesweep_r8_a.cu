@@ -1,15 +1,21 @@
-// onesweep_r8_a.cu -- 8-bit-digit kernel shapes, part A of the table assembled in onesweep_r8.cu
-// (variants 0-28: the default, the warp-multisplit shapes of the `block` knob, LPC / persistent-pipelined LPC / LPC32 shapes).
-// The table is split over three translation units only so that they compile in parallel.
+// onesweep_r8_a.cu -- 8-bit-digit kernel shapes, part A of the table assembled in onesweep_r8.cu.
+// The product build holds entries 0-2 only: the default, the north_star's warp-multisplit pass (kept as the reference
+// point of profiles/r01_microbench_rank_primitives.txt) and the non-persistent LPC32 pass.  Everything that was
+// measured and rejected is compiled with -DLSD_TUNING_VARIANTS (make TUNING=1) only.
 #include "onesweep_lpc32.cuh"
 #include "onesweep_lpc3.cuh"
+#ifdef LSD_TUNING_VARIANTS
 #include "onesweep_lpcp.cuh"
+#endif
 
 namespace lsd {
 
 static const OnesweepLauncher kPart[] = {
     make_lpc3_launcher<8, 9, 29, 3, 4, 0, 1, 1>(),  // 0: default -- persistent LPC32 pass, next tile prefetched into the dead counter matrix, ticket hand-over by mbarrier (= variant 75); peer-scatter / key-value / typed-key passes on onesweep_lpc32_kernel (= variant 68)
-    make_launcher<8, 128, 24, kMatchBallot>(),   // 1
+    make_launcher<8, 256, 16, kMatchBallot, true>(),   // 1: warp multisplit (8 ballots + popc), every form but peer-scatter
+    make_lpc32_launcher<8, 9, 29, 3>(),          // 2: non-persistent LPC32 pass, plain keys only
+#ifdef LSD_TUNING_VARIANTS
+    make_launcher<8, 128, 24, kMatchBallot>(),   // 3
     make_launcher<8, 256, 24, kMatchBallot, true>(),   // 2
     make_launcher<8, 1024, 8, kMatchBallot>(),   // 3
     make_launcher<8, 256, 16, kMatchBallot>(),   // 4
@@ -36,7 +42,8 @@ static const OnesweepLauncher kPart[] = {
     make_lpc32_launcher<8, 9, 21, 3>(),          // 25: tile 6048
     make_lpc_launcher<8, 9, 21, 4>(),            // 26: packed, tile 6048, 4 CTAs/SM
     make_lpc_launcher<8, 9, 23, 4>(),            // 27: packed, tile 6624, 4 CTAs/SM
-    make_launcher<8, 512, 16, kMatchBallot, true>(),   // 28: warp-multisplit (ballot) kernel, the round-1 v1 default
+    make_launcher<8, 512, 16, kMatchBallot, true>(),   // warp-multisplit (ballot) kernel, the round-1 v1 default
+#endif
 };
 
 const OnesweepLauncher* onesweep_r8_part_a(int* count)

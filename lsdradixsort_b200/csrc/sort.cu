@@ -108,20 +108,14 @@ const OnesweepLauncher* select_launcher(int r, int block, uint32_t variant, bool
     const OnesweepLauncher* t = table_for(r, &count);
     if (!t) return nullptr;
     if (variant != 0) return variant < (uint32_t)count ? &t[variant] : nullptr;
-    if (block <= 0) {  // the first entry that has the requested form (entry 0 has every form for r = 8; for r < 8 the key-value
-        for (int i = 0; i < count; ++i)  // forms live in the warp-multisplit entries behind it)
-            if (pass_fn(t[i], pairs, typed)) return &t[i];
-        return nullptr;
-    }
-    // `block` is the reference's threads-per-block knob: pick the warp-multisplit shape with exactly that many
-    // threads if there is one, else the shape (of any family) whose CTA size is closest.
-    const OnesweepLauncher* best = nullptr;
-    for (int i = 0; i < count; ++i) {
-        if (!pass_fn(t[i], pairs, typed)) continue;
-        if (t[i].mode == kMatchBallot && t[i].threads == block) return &t[i];
-        if (!best || std::abs(t[i].threads - block) < std::abs(best->threads - block)) best = &t[i];
-    }
-    return best;
+    // `block` is the reference's threads-per-block knob (LSDRadixSort.cu:839).  Here it is a HINT: every value gets the
+    // tuned default shape -- the first entry that has the requested form (entry 0 has every form for r = 8; for r < 8 the
+    // key-value forms live in the warp-multisplit entry behind it) -- so that a drop-in caller passing the reference's
+    // B = 128 ... 1024 is not slower than one passing 0.  Exact shapes are selected with lsd_sort_options.variant.
+    (void)block;
+    for (int i = 0; i < count; ++i)
+        if (pass_fn(t[i], pairs, typed)) return &t[i];
+    return nullptr;
 }
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -130,7 +124,7 @@ int make_layout(uint64_t n, int r, int block, const lsd_sort_options* opt, SortL
 {
     if (!valid_radix(r)) return LSD_ERR_INVALID_VALUE;
     if (block < 0 || block > 1024) return LSD_ERR_INVALID_VALUE;
-    if (n >= (1ull << 32)) return LSD_ERR_UNSUPPORTED;  // 32-bit scatter indices in this build
+    if (n > (1ull << 32)) return LSD_ERR_UNSUPPORTED;  // key positions are 32-bit (n = 2^32 included: the last position is 2^32 - 1)
     const uint32_t variant = opt ? opt->variant : 0u;
     const uint32_t key_type = opt ? opt->key_type : 0u;
     if (key_type > LSD_KEY_F32) return LSD_ERR_INVALID_VALUE;

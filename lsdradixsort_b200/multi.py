@@ -105,7 +105,9 @@ class MultiSorter:
     COLLECTIVE to construct and to call.  ``recv`` is this rank's receive buffer (CUDA int32 tensor; it is exported with
     CUDA IPC and mapped by the other ranks, so it must come from its own allocation, e.g. ``torch.empty``)."""
 
-    def __init__(self, recv: torch.Tensor, r: int = 8, group: Optional[dist.ProcessGroup] = None):
+    def __init__(self, recv: torch.Tensor, r: int = 8, group: Optional[dist.ProcessGroup] = None,
+                 max_n_local: Optional[int] = None):
+        """``max_n_local``: the most keys this rank will ever bring to ``sort`` (default: ``recv.numel()``)."""
         from . import _native as N
         from . import api
 
@@ -139,8 +141,9 @@ class MultiSorter:
         self._comm = N.MultiComm(C.sizeof(N.MultiComm), self.rank, self.nranks, self._cb[0], self._cb[1], None)
         self._ctx = C.c_void_p()
         self._scratch = torch.empty(recv.numel(), dtype=torch.int32, device=recv.device)
-        self._check(N.lib().lsd_multi_ctx_create(C.byref(self._comm), recv.data_ptr(), recv.numel(), r, C.byref(self._ctx),
-                                                 api._stream_ptr(recv.device)), "lsd_multi_ctx_create")
+        self._check(N.lib().lsd_multi_ctx_create(C.byref(self._comm), recv.data_ptr(), recv.numel(),
+                                                 recv.numel() if max_n_local is None else int(max_n_local), r,
+                                                 C.byref(self._ctx), api._stream_ptr(recv.device)), "lsd_multi_ctx_create")
 
     def _check(self, status: int, where: str) -> None:
         if status == self.N.LSD_ERR_COMM and self._error is not None:

@@ -50,7 +50,7 @@ def _worker(rank, world, port, kind, n_local, q):
         assert torch.equal(src.cpu(), torch.from_numpy(keys_np.view(np.int32))), "lsd_sort_multi must not modify its input"
         # an undersized receive buffer: every rank gets the same status, nothing is moved
         small = torch.empty(max(64, n_local // 2), dtype=torch.int32, device=dev)
-        tiny = multi.MultiSorter(small)
+        tiny = multi.MultiSorter(small, max_n_local=n_local)
         small.fill_(7)
         try:
             tiny.sort(src)
@@ -75,7 +75,7 @@ def _run(world, kind, n_local):
     procs = [ctx.Process(target=_worker, args=(r, world, port, kind, n_local, q)) for r in range(world)]
     for p in procs:
         p.start()
-    results = sorted((q.get(timeout=600) for _ in range(world)), key=lambda t: t[0])
+    results = sorted((q.get(timeout=240) for _ in range(world)), key=lambda t: t[0])
     for p in procs:
         p.join(120)
         assert p.exitcode == 0

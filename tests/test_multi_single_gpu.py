@@ -67,7 +67,7 @@ def _rank_main(rank, comm, keys_np, capacity, results, errors):
         recv = torch.full((capacity,), 0x5A5A5A5A, dtype=torch.int32, device="cuda")
         scratch = torch.empty(capacity, dtype=torch.int32, device="cuda")
         ctx = C.c_void_p()
-        st = lib.lsd_multi_ctx_create(C.byref(mc), recv.data_ptr(), capacity, 8, C.byref(ctx), api._stream_ptr(src.device))
+        st = lib.lsd_multi_ctx_create(C.byref(mc), recv.data_ptr(), capacity, src.numel(), 8, C.byref(ctx), api._stream_ptr(src.device))
         assert st == N.LSD_OK, st
         n_out = C.c_uint64(0)
         st = lib.lsd_sort_multi(ctx, src.data_ptr(), src.numel(), scratch.data_ptr(), C.byref(n_out), api._stream_ptr(src.device))

@@ -57,7 +57,7 @@ def test_typed_abi_validation_without_cuda():
     big = 1 << 30
     bad_type = N.SortOptions(C.sizeof(N.SortOptions), 0, 0, 0, 0, 7, 0)
     assert lib.lsd_sort_ex(0x1000, 0x2000, 16, 8, 0, 0x3000, big, C.byref(bad_type), None) == N.LSD_ERR_INVALID_VALUE
-    cpc_typed = N.SortOptions(C.sizeof(N.SortOptions), 0, 0, 32, 0, N.LSD_KEY_F32, 0)  # a variant without the mapping
+    cpc_typed = N.SortOptions(C.sizeof(N.SortOptions), 0, 0, 2, 0, N.LSD_KEY_F32, 0)  # variant 2: no typed-key mapping
     assert lib.lsd_sort_ex(0x1000, 0x2000, 16, 8, 0, 0x3000, big, C.byref(cpc_typed), None) == N.LSD_ERR_UNSUPPORTED
 
 

@@ -95,7 +95,7 @@ int main(int argc, char** argv)
             lsd_multi_comm comm;
             lsd_multi_comm_from_nccl(&state, comms[rank], rank, gpus, token, &comm);
             lsd_multi_ctx* ctx = nullptr;
-            int st = lsd_multi_ctx_create(&comm, recv, capacity, 8, &ctx, (lsd_stream_t)s);
+            int st = lsd_multi_ctx_create(&comm, recv, capacity, n_local, 8, &ctx, (lsd_stream_t)s);
             if (st != LSD_OK) {
                 std::fprintf(stderr, "rank %d: lsd_multi_ctx_create: %s (cuda %d)\n", rank, lsd_status_string(st), lsd_last_cuda_error());
                 ++failures;
