@@ -31,7 +31,7 @@ t = trace.cpu().numpy().reshape(tiles, 16).astype(np.float64)
 t = t[200:-200]  # steady state
 names = {0: "ticket+clear", 1: "tile landed", 2: "w0 counted", 3: "count barrier", 4: "scan1+digit scan", 5: "scan2 done",
          6: "w0 ranked", 7: "w0 scattered", 8: "lookback start", 9: "lookback done", 10: "chain complete", 13: "lookback rounds", 14: "lookback hops",
-         11: "final barrier", 12: "w0 stores issued"}
+         11: "final barrier", 12: "w0 stores issued", 15: "lookback load wait (sum)"}
 if args.family == "wide":
     names = {1: "tile landed", 2: "w0 counted", 3: "count barrier", 4: "scan1+digit scan", 5: "scan2 done", 6: "w0 ranked+scattered",
              7: "barrier C passed", 8: "lookback start", 9: "lookback done", 10: "chain tail (last warp)", 11: "chain tail (last-1)",

@@ -1,27 +1,20 @@
-// onesweep_lpc3.cuh -- LPC32 pass as a PERSISTENT kernel that prefetches its next tile.
+// onesweep_lpc4.cuh -- the persistent LPC pass (onesweep_lpc3.cuh) with TWO rank chains and a wider look-back window.
 //
-// In onesweep_lpc32_kernel a CTA lives for one tile: ticket, TMA load (~2 K cycles of DRAM latency under load), rank,
-// look-back, copy-out, exit.  The counter matrix is dead from the end of the rank chain on, while the reorder buffer is
-// still being streamed out.  Here a CTA loops over tickets and, right after the barrier that ends the ranking of tile k,
-// takes the ticket of tile k+1 and lets the TMA engine load it INTO THE DEAD MATRIX (+ tile-count area; together they
-// hold a tile) while tile k streams out.  Price: the matrix can only be cleared after the keys have been read out of it
-// (two more CTA-wide barriers per tile, and the clear no longer hides behind the load).
-// Plain and typed-key passes; same tile, look-back protocol and workspace layout as onesweep_lpc32_kernel.
-// Digits narrower than 8 bits (r = 1, 2, 4: the reference's other radix settings) have a counter matrix far smaller than a
-// tile, so there the prefetch goes to a dedicated second tile buffer (the shared-memory budget per CTA is the same) and the
-// digit shift is a run-time value (SHIFT < 0) to keep the number of instantiations down.
+// Why (profiles/r02_wide_pass_study.txt, bench_tools/trace.py on onesweep_lpc4_kernel): a tile of the round-1 default lives
+// 18.8 K cycles, of which the rank chain is 8.6 K (9 turns x 29 returning shared atomics, one in flight per warp, ~33
+// cycles each) and the look-back walk 10.7 K (28 hops, 9 rounds of 4 records); the chain's tail warps are the look-back
+// warps, so the two serial stretches end together at ~15.5 K and neither alone moves the pass.  Here both shrink at once:
+//   * cnt[digit][lane] keeps TWO 16-bit byte-offset counters per word -- low half: even warps, high half: odd warps; a
+//     lane's segment of the tile is [even warps' keys | odd warps' keys] -- so the even and the odd warps form two
+//     chains that run concurrently (5 + 4 turns);
+//   * the scatter follows its atomic one step behind inside the turn instead of keeping 15 packed rank registers, which
+//     frees the registers for a look-back window of 8 records per round (half the rounds).
+// Same tile, workspace layout, look-back protocol, prefetch of the next tile into the dead counter matrix and key flavours
+// (plain / typed) as onesweep_lpc4_kernel; 8-bit digits only (r < 8 stays on onesweep_lpc4_kernel).
 #pragma once
-#include "onesweep_lpc32.cuh"
+#include "onesweep_lpc3.cuh"
 
 namespace lsd {
-
-// 32 KiB of zeros in global memory: source of the TMA zero-fill of the counter matrix (CLR == 2)
-static __device__ __align__(128) uint4 g_lsd_zero_page[2048];
-
-__device__ __forceinline__ void mbar_arrive_release(uint64_t* bar)
-{
-    asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
 
 // CLR: 0 = matrix cleared with 128-bit stores, 1 = st.bulk, 2 = TMA copy of a zero page (keeps the clear off the LSU pipe)
 // NOB5: 1 = no CTA-wide barrier at the end of a tile: the next ticket is handed over through a second mbarrier
@@ -30,7 +23,7 @@ __device__ __forceinline__ void mbar_arrive_release(uint64_t* bar)
 //        reads alone cost ~7 % of the pass (0.665 -> 0.715 ms), so only the tuning variant carries them.
 template <int RB, int WARPS, int ITEMS, int MINB, int SHIFT, int LB, int CLR, int NOB5 = 0, bool TYPED = false, bool TRACE = false>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
-onesweep_lpc3_kernel(const PassArgs a)
+onesweep_lpc4_kernel(const PassArgs a)
 {
     using S_ = Lpc32Shape<RB, WARPS, ITEMS>;
     constexpr int H = S_::H, THREADS = S_::THREADS, S = S_::S, TILE = S_::TILE;
@@ -39,6 +32,10 @@ onesweep_lpc3_kernel(const PassArgs a)
     constexpr bool ALIAS = S_::OFF_DP - S_::OFF_MAT >= TILE;  // the dead matrix (+ tile counts) can hold the incoming tile
     constexpr int IN_OFF = (S_::WORDS + 3) & ~3;               // else: a dedicated prefetch buffer behind everything
     static_assert(LBT >= H / 2, "one digit pair per look-back thread");
+    static_assert(RB == 8, "8-bit digits only");
+    constexpr int EVEN = (WARPS + 1) / 2;  // warps of the even chain; they own the first EVEN*ITEMS keys of a lane segment
+    static_assert(SW >= 2, "warps 0 and 1 (the heads of the two chains) are scan warps");
+    static_assert(EVEN * ITEMS * 32 * 4 < 65536, "a row half must not carry into the other half");
     const int shift = SHIFT >= 0 ? SHIFT : a.shift;
 
     if (a.plan->skip[a.pass]) return;
@@ -57,6 +54,9 @@ onesweep_lpc3_kernel(const PassArgs a)
     const uint32_t tid = threadIdx.x;
     const uint32_t lane = tid & 31u;
     const uint32_t warp = tid >> 5;
+    const uint32_t half = warp & 1u;
+    const uint32_t inc4 = half ? (4u << 16) : 4u;  // this warp's counter half, in bytes
+    const uint32_t seg_off = lane * (uint32_t)S + (half ? (uint32_t)(EVEN * ITEMS) : 0u) + (warp >> 1) * (uint32_t)ITEMS;
 
     const bool src_scratch = a.plan->src_is_scratch[a.pass] != 0;
     const uint32_t* __restrict__ in = (src_scratch ? a.scratch : a.keys) + a.portion_base;
@@ -123,7 +123,7 @@ onesweep_lpc3_kernel(const PassArgs a)
         // ---- 1. lane-blocked read, then the matrix takes its place back ----
         uint32_t key[ITEMS];
         {
-            const uint32_t* src = s_in + lane * S + warp * ITEMS;
+            const uint32_t* src = s_in + seg_off;
 #pragma unroll
             for (int i = 0; i < ITEMS; ++i) key[i] = TYPED ? key_to_unsigned(src[i], xin) : src[i];
         }
@@ -151,7 +151,7 @@ onesweep_lpc3_kernel(const PassArgs a)
         if (warp == 0) LSD_TRACE(0);  // keys read, matrix cleared
 #pragma unroll
         for (int i = 0; i < ITEMS; ++i)
-            atomicAdd(reinterpret_cast<uint32_t*>(mat_bytes + cell_of(key[i])), 4u);
+            atomicAdd(reinterpret_cast<uint32_t*>(mat_bytes + cell_of(key[i])), inc4);
         if (warp == 0) LSD_TRACE(2);
         __syncthreads();  // counts complete
         if (warp == 0) LSD_TRACE(3);
@@ -179,7 +179,8 @@ onesweep_lpc3_kernel(const PassArgs a)
                     for (int k = 0; k < 8; ++k) {
                         const uint32_t grp = (q + k) & 7u;
                         const uint4 v = r4[grp];
-                        const uint32_t s = v.x + v.y + v.z + v.w;
+                        const uint32_t t = v.x + v.y + v.z + v.w;         // both halves at once (no carry, see EVEN)
+                        const uint32_t s = (t & 0xFFFFu) + (t >> 16);
                         total[g] += s;
                         if (grp < q) below[g] += s;
                     }
@@ -231,11 +232,11 @@ onesweep_lpc3_kernel(const PassArgs a)
                         const uint32_t grp = (q + k) & 7u;
                         if (grp == 0) run = start[g];
                         const uint4 v = r4[grp];
-                        uint4 o;
-                        o.x = run; run += v.x;
-                        o.y = run; run += v.y;
-                        o.z = run; run += v.z;
-                        o.w = run; run += v.w;
+                        uint4 o;  // low half: where the even warps' keys of this cell start; high half: the odd warps'
+                        o.x = run | ((run + (v.x & 0xFFFFu)) << 16); run += (v.x & 0xFFFFu) + (v.x >> 16);
+                        o.y = run | ((run + (v.y & 0xFFFFu)) << 16); run += (v.y & 0xFFFFu) + (v.y >> 16);
+                        o.z = run | ((run + (v.z & 0xFFFFu)) << 16); run += (v.z & 0xFFFFu) + (v.z >> 16);
+                        o.w = run | ((run + (v.w & 0xFFFFu)) << 16); run += (v.w & 0xFFFFu) + (v.w >> 16);
                         r4[grp] = o;
                     }
                 }
@@ -316,25 +317,23 @@ onesweep_lpc3_kernel(const PassArgs a)
         }
 
         if (warp == (uint32_t)WARPS - 1) LSD_TRACE(9);  // look-back done (last warp)
-        // ---- 2. rank chain ----
-        uint32_t rk[(ITEMS + 1) / 2];
-        if (warp > 0) named_bar_sync(warp, 64);
-#pragma unroll
-        for (int i = 0; i < ITEMS; ++i) {
-            const uint32_t old = atomicAdd(reinterpret_cast<uint32_t*>(mat_bytes + cell_of(key[i])), 4u);
-            if (i & 1) rk[i >> 1] = __byte_perm(rk[i >> 1], old, 0x5410); else rk[i >> 1] = old;
-        }
-        if (warp + 1 < (uint32_t)WARPS) named_bar_arrive(warp + 1, 64);
-        if (warp == 0) LSD_TRACE(6);
-        if (warp == (uint32_t)WARPS - 1) LSD_TRACE(10);
+        // ---- 2. two rank chains: even warps on the low halves, odd warps on the high halves; the scatter of a key
+        // ---- follows its atomic one step behind (a warp has one returning shared atomic in flight anyway) ----
+        if (warp >= 2u) named_bar_sync(warp, 64);
         {
             char* kb = reinterpret_cast<char*>(s_keys);
+            uint32_t prev = 0;
 #pragma unroll
             for (int i = 0; i < ITEMS; ++i) {
-                const uint32_t off = (i & 1) ? (rk[i >> 1] >> 16) : (rk[i >> 1] & 0xFFFFu);
-                *reinterpret_cast<uint32_t*>(kb + off) = key[i];
+                const uint32_t old = atomicAdd(reinterpret_cast<uint32_t*>(mat_bytes + cell_of(key[i])), inc4);
+                if (i > 0) *reinterpret_cast<uint32_t*>(kb + (half ? (prev >> 16) : (prev & 0xFFFFu))) = key[i - 1];
+                prev = old;
             }
+            if (warp + 2u < (uint32_t)WARPS) named_bar_arrive(warp + 2u, 64);
+            *reinterpret_cast<uint32_t*>(kb + (half ? (prev >> 16) : (prev & 0xFFFFu))) = key[ITEMS - 1];
         }
+        if (warp == 0) LSD_TRACE(6);
+        if (warp == (uint32_t)WARPS - 1) LSD_TRACE(10);
         // generic accesses to the matrix / tile counts are ordered before the async-proxy write of the next tile
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();  // reorder buffer complete; the matrix is dead
@@ -367,10 +366,10 @@ onesweep_lpc3_kernel(const PassArgs a)
 }
 
 template <int RB, int WARPS, int ITEMS, int MINB, int SHIFT, int LB, int CLR, int NOB5, bool TYPED, bool TRACE>
-int onesweep_lpc3_launch_shift(const PassArgs& a, cudaStream_t s)
+int onesweep_lpc4_launch_shift(const PassArgs& a, cudaStream_t s)
 {
     using S_ = Lpc32Shape<RB, WARPS, ITEMS>;
-    auto kern = onesweep_lpc3_kernel<RB, WARPS, ITEMS, MINB, SHIFT, LB, CLR, NOB5, TYPED, TRACE>;
+    auto kern = onesweep_lpc4_kernel<RB, WARPS, ITEMS, MINB, SHIFT, LB, CLR, NOB5, TYPED, TRACE>;
     constexpr bool ALIAS = S_::OFF_DP - S_::OFF_MAT >= S_::TILE;
     constexpr size_t SMEM = ALIAS ? S_::SMEM_BYTES : sizeof(uint32_t) * (((S_::WORDS + 3) & ~3) + S_::TILE) + 16;
     LSD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
@@ -383,41 +382,41 @@ int onesweep_lpc3_launch_shift(const PassArgs& a, cudaStream_t s)
 }
 
 template <int RB, int WARPS, int ITEMS, int MINB, int LB, int CLR, int NOB5, bool TYPED = false, bool TRACE = false>
-int onesweep_lpc3_launch(const PassArgs& a, cudaStream_t s)
+int onesweep_lpc4_launch(const PassArgs& a, cudaStream_t s)
 {
-    if constexpr (RB != 8) return onesweep_lpc3_launch_shift<RB, WARPS, ITEMS, MINB, -1, LB, CLR, NOB5, TYPED, TRACE>(a, s);
+    if constexpr (RB != 8) return onesweep_lpc4_launch_shift<RB, WARPS, ITEMS, MINB, -1, LB, CLR, NOB5, TYPED, TRACE>(a, s);
     switch (a.shift) {
-        case 0: return onesweep_lpc3_launch_shift<RB, WARPS, ITEMS, MINB, 0, LB, CLR, NOB5, TYPED, TRACE>(a, s);
-        case 8: return onesweep_lpc3_launch_shift<RB, WARPS, ITEMS, MINB, 8, LB, CLR, NOB5, TYPED, TRACE>(a, s);
-        case 16: return onesweep_lpc3_launch_shift<RB, WARPS, ITEMS, MINB, 16, LB, CLR, NOB5, TYPED, TRACE>(a, s);
-        case 24: return onesweep_lpc3_launch_shift<RB, WARPS, ITEMS, MINB, 24, LB, CLR, NOB5, TYPED, TRACE>(a, s);
+        case 0: return onesweep_lpc4_launch_shift<RB, WARPS, ITEMS, MINB, 0, LB, CLR, NOB5, TYPED, TRACE>(a, s);
+        case 8: return onesweep_lpc4_launch_shift<RB, WARPS, ITEMS, MINB, 8, LB, CLR, NOB5, TYPED, TRACE>(a, s);
+        case 16: return onesweep_lpc4_launch_shift<RB, WARPS, ITEMS, MINB, 16, LB, CLR, NOB5, TYPED, TRACE>(a, s);
+        case 24: return onesweep_lpc4_launch_shift<RB, WARPS, ITEMS, MINB, 24, LB, CLR, NOB5, TYPED, TRACE>(a, s);
     }
     return LSD_ERR_INVALID_VALUE;
 }
 
-constexpr int kModeLpc3 = 6;
+constexpr int kModeLpc4 = 8;
 
 // FORMS: 0 = plain passes only (tuning variants); 1 = the r = 8 default entry: plain and typed-key passes on the persistent
 // kernel, peer-scatter and key-value passes on onesweep_lpc32_kernel (same tile size, workspace layout and look-back protocol);
 // 2 = plain and typed-key passes (the r < 8 default entries; key-value sorts there use the warp-multisplit entries).
 template <int RB, int WARPS, int ITEMS, int MINB, int LB, int CLR = 0, int NOB5 = 0, int FORMS = 0, bool TRACE = false>
-constexpr OnesweepLauncher make_lpc3_launcher()
+constexpr OnesweepLauncher make_lpc4_launcher()
 {
     using S_ = Lpc32Shape<RB, WARPS, ITEMS>;
     if constexpr (FORMS == 1)
-        return OnesweepLauncher{RB, S_::THREADS, ITEMS, kModeLpc3, (uint32_t)S_::TILE, S_::PORTION_MAX, S_::SMEM_BYTES,
-                                &onesweep_lpc3_launch<RB, WARPS, ITEMS, MINB, LB, CLR, NOB5>,
+        return OnesweepLauncher{RB, S_::THREADS, ITEMS, kModeLpc4, (uint32_t)S_::TILE, S_::PORTION_MAX, S_::SMEM_BYTES,
+                                &onesweep_lpc4_launch<RB, WARPS, ITEMS, MINB, LB, CLR, NOB5>,
                                 &onesweep_lpc32_launch<RB, WARPS, ITEMS, MINB, LB, 5, kPassPeer, false>,
                                 &onesweep_lpc32_launch<RB, WARPS, ITEMS, MINB, LB, 5, kPassPairs, false>,
-                                &onesweep_lpc3_launch<RB, WARPS, ITEMS, MINB, LB, CLR, NOB5, true>,
+                                &onesweep_lpc4_launch<RB, WARPS, ITEMS, MINB, LB, CLR, NOB5, true>,
                                 &onesweep_lpc32_launch<RB, WARPS, ITEMS, MINB, LB, 5, kPassPairsTyped, false>};
     else if constexpr (FORMS == 2)
-        return OnesweepLauncher{RB, S_::THREADS, ITEMS, kModeLpc3, (uint32_t)S_::TILE, S_::PORTION_MAX, S_::SMEM_BYTES,
-                                &onesweep_lpc3_launch<RB, WARPS, ITEMS, MINB, LB, CLR, NOB5>, nullptr, nullptr,
-                                &onesweep_lpc3_launch<RB, WARPS, ITEMS, MINB, LB, CLR, NOB5, true>, nullptr};
+        return OnesweepLauncher{RB, S_::THREADS, ITEMS, kModeLpc4, (uint32_t)S_::TILE, S_::PORTION_MAX, S_::SMEM_BYTES,
+                                &onesweep_lpc4_launch<RB, WARPS, ITEMS, MINB, LB, CLR, NOB5>, nullptr, nullptr,
+                                &onesweep_lpc4_launch<RB, WARPS, ITEMS, MINB, LB, CLR, NOB5, true>, nullptr};
     else
-        return OnesweepLauncher{RB, S_::THREADS, ITEMS, kModeLpc3, (uint32_t)S_::TILE, S_::PORTION_MAX, S_::SMEM_BYTES,
-                                &onesweep_lpc3_launch<RB, WARPS, ITEMS, MINB, LB, CLR, NOB5, false, TRACE>, nullptr, nullptr, nullptr,
+        return OnesweepLauncher{RB, S_::THREADS, ITEMS, kModeLpc4, (uint32_t)S_::TILE, S_::PORTION_MAX, S_::SMEM_BYTES,
+                                &onesweep_lpc4_launch<RB, WARPS, ITEMS, MINB, LB, CLR, NOB5, false, TRACE>, nullptr, nullptr, nullptr,
                                 nullptr};
 }
 

@@ -5,6 +5,7 @@
 #include "onesweep_lpc32.cuh"
 #include "onesweep_lpc3.cuh"
 #ifdef LSD_TUNING_VARIANTS
+#include "onesweep_lpc4.cuh"
 #include "onesweep_lpcp.cuh"
 #endif
 
@@ -15,6 +16,9 @@ static const OnesweepLauncher kPart[] = {
     make_launcher<8, 256, 16, kMatchBallot, true>(),   // 1: warp multisplit (8 ballots + popc), every form but peer-scatter
     make_lpc32_launcher<8, 9, 29, 3>(),          // 2: non-persistent LPC32 pass, plain keys only
 #ifdef LSD_TUNING_VARIANTS
+    make_lpc4_launcher<8, 9, 29, 3, 8, 0, 1>(),  // 3: persistent pass with two rank chains, look-back window 8 (round 2: no gain, see profiles/r02_wide_pass_study.txt)
+    make_lpc4_launcher<8, 9, 29, 3, 4, 0, 1>(),  // 4: two rank chains, window 4
+    make_lpc4_launcher<8, 9, 29, 3, 8, 0, 1, 0, true>(),  // 5: 3 with the per-tile phase trace
     make_launcher<8, 128, 24, kMatchBallot>(),   // 3
     make_launcher<8, 256, 24, kMatchBallot, true>(),   // 2
     make_launcher<8, 1024, 8, kMatchBallot>(),   // 3
