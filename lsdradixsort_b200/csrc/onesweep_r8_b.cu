@@ -16,13 +16,7 @@ static const OnesweepLauncher kPart[] = {
     make_cpc_launcher<8, 64, 3, 4>(),            // 34: look-back window 4
     make_cpc_launcher<8, 48, 3, 8>(),            // 35: tile 6144
     make_cpc_launcher<8, 32, 4, 8>(),            // 36: tile 4096, 4 CTAs/SM
-    make_cpc_launcher<8, 64, 3, 0>(),            // 37: TIMING EXPERIMENT, no look-back (output wrong)
     make_cpc_launcher<8, 64, 3, 32>(),           // 38: look-back window 32
-    make_cpc_launcher<8, 64, 3, 0, 2>(),         // 39: TIMING: no look-back, full-line stores
-    make_cpc_launcher<8, 64, 3, 0, 4>(),         // 40: TIMING: no look-back, no global stores
-    make_cpc_launcher<8, 64, 3, 0, 8>(),         // 41: TIMING: no look-back, conflict-free smem scatter
-    make_cpc_launcher<8, 64, 3, 0, 10>(),        // 42: TIMING: no look-back, conflict-free scatter, full-line stores
-    make_cpc_launcher<8, 64, 3, 0, 12>(),        // 43: TIMING: no look-back, conflict-free scatter, no stores
     make_cpcp_launcher<8, 64, 4, 8, 152>(),      // 44: persistent pipeline, 4 buffers, front groups at 152 registers
     make_cpcp_launcher<8, 64, 4, 8, 0>(),        // 45: same without register reallocation
     make_cpcp_launcher<8, 64, 4, 4, 152>(),      // 46: look-back window 4

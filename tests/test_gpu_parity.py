@@ -97,8 +97,6 @@ def test_sort_kernel_variants_r8(variant, kind):
     LSDSORT_LIB=lsdradixsort_b200/liblsdsort_tuning.so) appends the measured-and-rejected families."""
     if not _variant_exists(variant):
         pytest.skip("variant not in this build of liblsdsort (tuning variants: make TUNING=1)")
-    if variant in (39, 41, 42, 43, 44, 45):
-        pytest.skip("timing experiment (output wrong on purpose)")
     n = 300_000 + 11
     keys = keygen.make_keys(kind, n, seed=variant)
     d = dev(keys)
