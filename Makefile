@@ -11,7 +11,7 @@ OBJDIR  := build/obj
 # lsd_sort_options.variant values: a separate library, lsdradixsort_b200/liblsdsort_tuning.so (use it with
 # LSDSORT_LIB=...; bench_tools/ and the variant tests need it).  The product library holds the shipped shapes only.
 TUNING  ?= 0
-SRCS    := api.cu multi.cu sort.cu histogram.cu scan.cu onesweep_r1.cu onesweep_r2.cu onesweep_r4.cu onesweep_r8.cu onesweep_r8_a.cu
+SRCS    := api.cu multi.cu sort.cu keys64.cu histogram.cu scan.cu onesweep_r1.cu onesweep_r2.cu onesweep_r4.cu onesweep_r8.cu onesweep_r8_a.cu
 ifeq ($(TUNING),1)
 SRCS    += onesweep_r8_b.cu onesweep_r8_c.cu onesweep_r8_d.cu
 NVFLAGS += -DLSD_TUNING_VARIANTS

@@ -126,7 +126,10 @@ typedef struct lsd_sort_options {
  *                the sign bit of the others) -- equal to `<` on floats wherever `<` decides.
  * Supported by the default kernel shapes (variant 0, any r, any block) of lsd_sort_ex / lsd_sort_pairs / *_timed;
  * other variants return LSD_ERR_UNSUPPORTED. */
-enum lsd_key_type { LSD_KEY_U32 = 0, LSD_KEY_I32 = 1, LSD_KEY_F32 = 2 };
+enum lsd_key_type {
+    LSD_KEY_U32 = 0, LSD_KEY_I32 = 1, LSD_KEY_F32 = 2,
+    LSD_KEY_U64 = 3, LSD_KEY_I64 = 4, LSD_KEY_F64 = 5 /* lsd_sort64 only */
+};
 
 LSD_API size_t lsd_sort_workspace_bytes(uint64_t n, int r, int block);
 LSD_API size_t lsd_sort_workspace_bytes_ex(uint64_t n, int r, int block, const lsd_sort_options *opt);
@@ -150,6 +153,17 @@ LSD_API int lsd_sort_pairs(uint32_t *keys, uint32_t *vals, uint32_t *keys_scratc
 LSD_API int lsd_sort_pairs_timed(uint32_t *keys, uint32_t *vals, uint32_t *keys_scratch, uint32_t *vals_scratch,
                                  uint64_t n, int r, int block, void *ws, size_t ws_bytes, const lsd_sort_options *opt,
                                  lsd_stream_t stream, float *stage_ms, int stage_cap, int *stages_written);
+
+/* 64-bit keys (the reference sorts uint32 only, LSDRadixSort.cu:62, :839).  keys: n 64-bit keys in,
+ * ascending out in the order key_type names (LSD_KEY_U64: unsigned; LSD_KEY_I64: two's complement; LSD_KEY_F64: IEEE
+ * total order, as LSD_KEY_F32).  scratch: n 64-bit entries of ping-pong space.  Eight stable 8-bit passes: the keys are
+ * split into low / high word arrays, every pass is the key-value pass of lsd_sort_pairs with the digit's word as the key
+ * and the other word as its value (16 B per key per pass, what a native 64-bit pass moves), and a final kernel merges
+ * the words back.  Digits that are constant over the input are skipped per word (keys below 2^32: four passes).
+ * n <= 2^32.  Workspace from lsd_sort64_workspace_bytes. */
+LSD_API size_t lsd_sort64_workspace_bytes(uint64_t n);
+LSD_API int lsd_sort64(uint64_t *keys, uint64_t *scratch, uint64_t n, uint32_t key_type, void *ws, size_t ws_bytes,
+                       lsd_stream_t stream);
 
 /* One stable counting-sort pass on digit `bit_group`: out <- in reordered by that digit, keys with
  * equal digits keeping their input order.  Replaces one iteration of the reference's pass loop

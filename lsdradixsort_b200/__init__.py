@@ -5,6 +5,7 @@ prefix_sum, LSD sort with radix bits R and block size B).  All compute is hand-w
 ``csrc/`` behind the C ABI of ``include/lsdsort.h``; this package is the host-side mirror.
 """
 from ._native import LsdError, LIB_PATH, build_library  # noqa: F401
+from . import api  # noqa: F401
 from .api import (  # noqa: F401
     BuildHistograms,
     GetGPUPrefixSumBlockSumsCount,
@@ -15,6 +16,8 @@ from .api import (  # noqa: F401
     argsort,
     sort_pairs_,
     Sorter,
+    Sorter64,
+    sort64_,
     SortInfo,
     build_histogram,
     digit_histograms,

@@ -24,6 +24,7 @@ LSD_ERR_ALIGNMENT = 5
 LSD_ERR_CAPACITY = 6
 LSD_ERR_COMM = 7
 LSD_KEY_U32, LSD_KEY_I32, LSD_KEY_F32 = 0, 1, 2
+LSD_KEY_U64, LSD_KEY_I64, LSD_KEY_F64 = 3, 4, 5
 
 
 class LsdError(RuntimeError):
@@ -127,6 +128,8 @@ def lib() -> C.CDLL:
             [vp, vp, vp, vp, C.c_uint64, C.c_int, C.c_int, vp, C.c_size_t, C.POINTER(SortOptions), vp,
              C.POINTER(C.c_float), C.c_int, C.POINTER(C.c_int)],
         ),
+        "lsd_sort64_workspace_bytes": (C.c_size_t, [C.c_uint64]),
+        "lsd_sort64": (C.c_int, [vp, vp, C.c_uint64, C.c_uint32, vp, C.c_size_t, vp]),
         "lsd_sort_pass": (C.c_int, [vp, vp, C.c_uint64, C.c_int, C.c_int, C.c_int, vp, C.c_size_t, vp, vp]),
         "lsd_sort_pass_scatter": (C.c_int, [vp, C.c_uint64, C.c_int, C.c_int, vp, vp, vp, C.c_size_t, vp]),
         "lsd_ipc_export": (C.c_int, [vp, vp, u64p]),

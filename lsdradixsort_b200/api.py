@@ -88,10 +88,23 @@ def BuildHistograms(a: torch.Tensor, h: torch.Tensor, count: int, r: int, bit_gr
     build_histogram(a[:count], r, bit_group, block, out=h)
 
 
+def digit_count(r: int) -> int:
+    """Digits of a 32-bit key at width ``r``: 32/r for 1, 2, 4, 8, 16; ceil(32/r) for the other (composite) widths,
+    whose top digit is narrower (r = 11: 11 + 11 + 10 bits)."""
+    return (32 + r - 1) // r
+
+
+def exec_radix(r: int) -> int:
+    """The digit width a FULL sort executes: composite widths (every r in 3..16 other than 4 and 8) run the 8-bit schedule
+    (the result of a full sort does not depend on r)."""
+    return r if r in (1, 2, 4, 8) else 8
+
+
 def digit_histograms(keys: torch.Tensor, r: int = 8) -> torch.Tensor:
-    """Whole-array histograms of every digit in one read: ``[32/r][2^r]`` int64."""
+    """Whole-array histograms of every digit: ``[digit_count(r)][2^r]`` int64 (one read of the keys for r = 1, 2, 4, 8;
+    one read per digit for the composite widths)."""
     _check_keys(keys, "keys")
-    out = torch.empty((32 // r, 1 << r), dtype=torch.int64, device=keys.device)
+    out = torch.empty((digit_count(r), 1 << r), dtype=torch.int64, device=keys.device)
     N.check(
         N.lib().lsd_digit_histograms(keys.data_ptr(), keys.numel(), r, out.data_ptr(), _stream_ptr(keys.device)),
         "lsd_digit_histograms",
@@ -250,7 +263,7 @@ class Sorter:
     def sort_timed_(self, keys: torch.Tensor) -> list:
         """Sort and return per-stage device milliseconds [hist+plan, pass0.., copy-back] (synchronises)."""
         _check_keys(keys, "keys", allow_float=True)
-        stages = 32 // self.r + 2
+        stages = 32 // exec_radix(self.r) + 2
         buf = (C.c_float * stages)()
         written = C.c_int(0)
         o = _options(**_typed_opts(keys, self.opts))
@@ -306,7 +319,7 @@ class PairSorter:
         return keys, vals
 
     def sort_timed_(self, keys: torch.Tensor, vals: torch.Tensor) -> list:
-        stages = 32 // self.r + 2
+        stages = 32 // exec_radix(self.r) + 2
         buf = (C.c_float * stages)()
         written = C.c_int(0)
         N.check(N.lib().lsd_sort_pairs_timed(*self._args(keys, vals), buf, stages, C.byref(written)),
@@ -335,6 +348,47 @@ def sort_(keys: torch.Tensor, r: int = 8, block: int = 0, **opts) -> torch.Tenso
     (the reference's order) unless ``key_type="i32"``; float32 tensors as floats (IEEE total order)."""
     _check_keys(keys, "keys", allow_float=True)
     return Sorter(keys.numel(), r, block, device=keys.device, **opts).sort_(keys)
+
+
+_KEY64_TYPES = {torch.int64: N.LSD_KEY_I64, torch.float64: N.LSD_KEY_F64}
+if hasattr(torch, "uint64"):
+    _KEY64_TYPES[torch.uint64] = N.LSD_KEY_U64
+_KEY64_NAMES = {"u64": N.LSD_KEY_U64, "i64": N.LSD_KEY_I64, "f64": N.LSD_KEY_F64}
+
+
+class Sorter64:
+    """64-bit keys (lsd_sort64): reusable ping-pong buffer + workspace for up to ``max_n`` keys."""
+
+    def __init__(self, max_n: int, device: Optional[torch.device] = None):
+        self.max_n = int(max_n)
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        nbytes = N.lib().lsd_sort64_workspace_bytes(self.max_n)
+        if nbytes == 0:
+            raise N.LsdError(N.LSD_ERR_UNSUPPORTED, "lsd_sort64_workspace_bytes", "n too large")
+        self.scratch = torch.empty(max(self.max_n, 2), dtype=torch.int64, device=self.device)
+        self.workspace = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=self.device)
+
+    def sort_(self, keys: torch.Tensor, key_type=None) -> torch.Tensor:
+        """Sort in place.  ``key_type``: "u64" / "i64" / "f64"; default by dtype (int64 signed, float64 IEEE total order,
+        uint64 unsigned)."""
+        if not isinstance(keys, torch.Tensor) or not keys.is_cuda:
+            raise TypeError("keys must be a CUDA tensor (this library has no CPU path)")
+        if keys.dtype not in _KEY64_TYPES or keys.dim() != 1 or not keys.is_contiguous():
+            raise TypeError("keys must be a contiguous 1-D int64/uint64/float64 tensor")
+        if keys.numel() > self.max_n:
+            raise ValueError("keys larger than this Sorter64's capacity")
+        kt = _KEY64_TYPES[keys.dtype] if key_type is None else (_KEY64_NAMES[key_type] if isinstance(key_type, str) else int(key_type))
+        N.check(
+            N.lib().lsd_sort64(keys.data_ptr(), self.scratch.data_ptr(), keys.numel(), kt, self.workspace.data_ptr(),
+                               self.workspace.numel(), _stream_ptr(keys.device)),
+            "lsd_sort64",
+        )
+        return keys
+
+
+def sort64_(keys: torch.Tensor, key_type=None) -> torch.Tensor:
+    """Sort a 64-bit key tensor in place; allocates scratch for this one call."""
+    return Sorter64(keys.numel(), device=keys.device if isinstance(keys, torch.Tensor) else None).sort_(keys, key_type)
 
 
 class HostSorter:

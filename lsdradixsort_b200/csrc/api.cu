@@ -1,4 +1,5 @@
 // api.cu -- the extern "C" surface declared in include/lsdsort.h.
+#include <algorithm>
 #include <new>
 
 #include "onesweep.cuh"
@@ -102,9 +103,10 @@ LSD_API int lsd_build_histogram(const uint32_t* keys, uint64_t n, int r, int bit
 
 LSD_API int lsd_digit_histograms(const uint32_t* keys, uint64_t n, int r, uint64_t* hist, lsd_stream_t stream)
 {
-    if (!valid_radix(r)) return LSD_ERR_INVALID_VALUE;
+    if (!accepted_radix(r)) return LSD_ERR_INVALID_VALUE;
     if (!hist || (n > 0 && !keys)) return LSD_ERR_INVALID_VALUE;
     if (n > 0 && !aligned_to(keys, 16)) return LSD_ERR_ALIGNMENT;
+    if (composite_radix(r)) return launch_digit_histograms_wide(keys, n, r, hist, (cudaStream_t)stream);
     return launch_digit_histograms(keys, n, r, hist, (cudaStream_t)stream);
 }
 
@@ -131,8 +133,11 @@ LSD_API int lsd_prefix_sum(uint32_t* a, uint64_t n, int block, void* ws, size_t 
 // ---- sort ----------------------------------------------------------------------------
 LSD_API size_t lsd_sort_workspace_bytes_ex(uint64_t n, int r, int block, const lsd_sort_options* opt)
 {
+    if (opt && opt->struct_bytes != sizeof(lsd_sort_options)) return 0;  // same check as lsd_sort_ex
     SortLayout L;
     if (make_layout(n, r, block, opt, &L) != LSD_OK) return 0;
+    // composite digit widths: lsd_sort_pass runs sub-passes through a temporary key array in the workspace
+    if (composite_radix(r)) return std::max(L.total_bytes, wide_pass_workspace_bytes(n));
     return L.total_bytes;
 }
 LSD_API size_t lsd_sort_workspace_bytes(uint64_t n, int r, int block)
@@ -165,14 +170,23 @@ LSD_API int lsd_sort_pairs(uint32_t* keys, uint32_t* vals, uint32_t* keys_scratc
 {
     if (opt && opt->struct_bytes != sizeof(lsd_sort_options)) return LSD_ERR_INVALID_VALUE;
     if (n > 0 && (!vals || !vals_scratch)) return LSD_ERR_INVALID_VALUE;
-    if (n == 0) return valid_radix(r) ? LSD_OK : LSD_ERR_INVALID_VALUE;
+    if (n == 0) return accepted_radix(r) ? LSD_OK : LSD_ERR_INVALID_VALUE;
     return sort_enqueue(keys, keys_scratch, n, r, block, ws, ws_bytes, opt, (cudaStream_t)stream, nullptr, nullptr, vals,
                         vals_scratch);
+}
+
+LSD_API size_t lsd_sort64_workspace_bytes(uint64_t n) { return sort64_workspace_bytes(n); }
+
+LSD_API int lsd_sort64(uint64_t* keys, uint64_t* scratch, uint64_t n, uint32_t key_type, void* ws, size_t ws_bytes,
+                       lsd_stream_t stream)
+{
+    return sort64_enqueue(keys, scratch, n, key_type, ws, ws_bytes, (cudaStream_t)stream);
 }
 
 LSD_API int lsd_sort_pass(const uint32_t* in, uint32_t* out, uint64_t n, int r, int bit_group, int block, void* ws,
                           size_t ws_bytes, uint64_t* hist_out, lsd_stream_t stream)
 {
+    if (composite_radix(r)) return pass_enqueue_wide(in, out, n, r, bit_group, ws, ws_bytes, hist_out, (cudaStream_t)stream);
     if (!valid_radix(r)) return LSD_ERR_INVALID_VALUE;
     return pass_enqueue(in, out, n, r, bit_group, block, ws, ws_bytes, hist_out, (cudaStream_t)stream);
 }
@@ -229,12 +243,19 @@ static int sort_timed_impl(uint32_t* keys, uint32_t* vals, uint32_t* scratch, ui
                            float* stage_ms, int stage_cap, int* stages_written)
 {
     if (opt && opt->struct_bytes != sizeof(lsd_sort_options)) return LSD_ERR_INVALID_VALUE;
-    if (!valid_radix(r) || !stage_ms) return LSD_ERR_INVALID_VALUE;
-    const int passes = 32 / r;
+    if (!accepted_radix(r) || !stage_ms) return LSD_ERR_INVALID_VALUE;
+    const int passes = 32 / exec_radix(r);  // composite digit widths run (and are reported as) the 8-bit schedule
     const int stages = passes + 2;
     if (stage_cap < stages) return LSD_ERR_INVALID_VALUE;
     cudaEvent_t ev[kMaxPasses + 3];
-    for (int i = 0; i < stages + 1; ++i) LSD_CUDA_TRY(cudaEventCreate(&ev[i]));
+    for (int i = 0; i < stages + 1; ++i) {
+        const cudaError_t e = cudaEventCreate(&ev[i]);
+        if (e != cudaSuccess) {  // do not leak the events created so far
+            for (int j = 0; j < i; ++j) cudaEventDestroy(ev[j]);
+            set_last_cuda_error(e);
+            return LSD_ERR_CUDA;
+        }
+    }
     int rc = LSD_OK;
     if (n == 0) {
         for (int i = 0; i < stages; ++i) stage_ms[i] = 0.f;
@@ -276,7 +297,8 @@ LSD_API int lsd_sort_pairs_timed(uint32_t* keys, uint32_t* vals, uint32_t* keys_
 LSD_API int lsd_sort_read_plan(const void* ws, uint64_t n, int r, uint32_t* skipped_mask, int* launches,
                                lsd_stream_t stream)
 {
-    if (!valid_radix(r)) return LSD_ERR_INVALID_VALUE;
+    if (!accepted_radix(r)) return LSD_ERR_INVALID_VALUE;
+    r = exec_radix(r);  // composite digit widths: the mask names the executed 8-bit passes
     if (skipped_mask) *skipped_mask = 0;
     if (launches) *launches = 0;
     if (n == 0) return LSD_OK;
@@ -308,7 +330,7 @@ struct lsd_host_ctx {
 
 LSD_API int lsd_host_ctx_create(uint64_t max_n, int r, int block, lsd_host_ctx** out)
 {
-    if (!out || !valid_radix(r)) return LSD_ERR_INVALID_VALUE;
+    if (!out || !accepted_radix(r)) return LSD_ERR_INVALID_VALUE;
     *out = nullptr;
     SortLayout L;
     const int st = make_layout(max_n, r, block, nullptr, &L);

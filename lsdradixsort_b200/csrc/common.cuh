@@ -109,7 +109,16 @@ void set_last_cuda_error(cudaError_t e);
 
 #define LSD_LAUNCH_CHECK() LSD_CUDA_TRY(cudaGetLastError())
 
-inline bool valid_radix(int r) { return r == 1 || r == 2 || r == 4 || r == 8; }
+inline bool valid_radix(int r) { return r == 1 || r == 2 || r == 4 || r == 8; }  // digit widths with their own pass kernels
+// Composite digit widths: every other r up to 16 (16 is the one factor of 32 the reference's CPU path takes beyond these,
+// LSDRadixSort.cu:56-69; 11 is the classic 11-11-10 split).  Digit i is bits [i*r, min(32, (i+1)*r)); there are
+// ceil(32/r) of them.  A stable pass on such a digit IS a stable pass on its low 8 bits followed by one on the rest, so
+// these widths run on the 8-bit pass kernel (sort.cu: pass_enqueue_wide); a full sort's result does not depend on r at
+// all and runs the 8-bit schedule.
+inline bool composite_radix(int r) { return r >= 3 && r <= 16 && !valid_radix(r); }
+inline bool accepted_radix(int r) { return valid_radix(r) || composite_radix(r); }
+inline int exec_radix(int r) { return composite_radix(r) ? 8 : r; }   // the digit width the full sort executes
+inline int digit_count(int r) { return (32 + r - 1) / r; }
 inline bool aligned_to(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; }
 
 int sm_count();          // cached multiprocessor count of the current device
@@ -121,6 +130,8 @@ int launch_digit_histograms(const uint32_t* keys, uint64_t n, int r, uint64_t* h
 int launch_top_digit_histogram(const uint32_t* keys, uint64_t n, int r, uint64_t* hist, cudaStream_t s);
 int launch_tile_histograms(const uint32_t* keys, uint64_t n, int r, int bit_group, int block, uint32_t* hist,
                            cudaStream_t s);
+int launch_field_histogram(const uint32_t* keys, uint64_t n, int shift, int bits, uint64_t* hist, cudaStream_t s);
+int launch_field_scan(uint64_t* a, int bits, cudaStream_t s);
 size_t scan_workspace_bytes(uint64_t n, int block);
 int launch_prefix_sum(uint32_t* a, uint64_t n, int block, void* ws, size_t ws_bytes, cudaStream_t s);
 

@@ -145,6 +145,99 @@ int launch_digit_histograms(const uint32_t* keys, uint64_t n, int r, uint64_t* h
 }
 
 // -------------------------------------------------------------------------------------
+// (1b) Histogram of an arbitrary bit field (shift, bits <= 16): the composite digit widths (r = 16, which the reference's
+//      CPU path accepts -- "any factor of 32", LSDRadixSort.cu:56-69 -- and the classic 11-11-10 split) and the
+//      sub-passes they run as.  Up to 12 bits the counters live in shared memory (conflicts between lanes are possible:
+//      this is not the hot path), wider fields count with 64-bit global atomics (512 KiB of counters: L2 resident).
+// -------------------------------------------------------------------------------------
+constexpr int kFieldThreads = 512;
+constexpr int kFieldSmemBits = 12;
+
+template <bool SMEM>
+__global__ void __launch_bounds__(kFieldThreads)
+field_hist_kernel(const uint32_t* __restrict__ keys, uint64_t n, int shift, uint32_t mask, unsigned long long* __restrict__ hist)
+{
+    extern __shared__ uint32_t fcnt[];
+    const uint32_t tid = threadIdx.x;
+    if constexpr (SMEM) {
+        for (uint32_t i = tid; i <= mask; i += kFieldThreads) fcnt[i] = 0;
+        __syncthreads();
+    }
+    auto add = [&](uint32_t key) {
+        const uint32_t d = (key >> shift) & mask;
+        if constexpr (SMEM) atomicAdd(fcnt + d, 1u);
+        else atomicAdd(hist + d, 1ull);
+    };
+    const uint64_t nvec = n >> 2;
+    const uint64_t stride = (uint64_t)gridDim.x * kFieldThreads;
+    for (uint64_t i = (uint64_t)blockIdx.x * kFieldThreads + tid; i < nvec; i += stride) {
+        const uint4 a = ld_stream_v4(keys + 4 * i);
+        add(a.x); add(a.y); add(a.z); add(a.w);
+    }
+    if (blockIdx.x == 0) {
+        const uint64_t t = (nvec << 2) + tid;
+        if (t < n) add(keys[t]);
+    }
+    if constexpr (SMEM) {
+        __syncthreads();
+        for (uint32_t i = tid; i <= mask; i += kFieldThreads)
+            if (fcnt[i]) atomicAdd(hist + i, (unsigned long long)fcnt[i]);
+    }
+}
+
+// hist[0 .. 2^bits) (uint64) <- counts of ((key >> shift) & (2^bits - 1)); overwritten
+int launch_field_histogram(const uint32_t* keys, uint64_t n, int shift, int bits, uint64_t* hist, cudaStream_t s)
+{
+    if (bits < 1 || bits > 16 || shift < 0 || shift + bits > 32) return LSD_ERR_INVALID_VALUE;
+    LSD_CUDA_TRY(cudaMemsetAsync(hist, 0, sizeof(uint64_t) << bits, s));
+    if (n == 0) return LSD_OK;
+    const uint32_t mask = (1u << bits) - 1u;
+    const uint64_t slices = ((n >> 2) + kFieldThreads - 1) / kFieldThreads;
+    uint64_t grid = (uint64_t)sm_count() * 4;
+    if (grid > slices) grid = slices ? slices : 1;
+    if (bits <= kFieldSmemBits)
+        field_hist_kernel<true><<<(int)grid, kFieldThreads, sizeof(uint32_t) << bits, s>>>(keys, n, shift, mask,
+                                                                                        reinterpret_cast<unsigned long long*>(hist));
+    else
+        field_hist_kernel<false><<<(int)grid, kFieldThreads, 0, s>>>(keys, n, shift, mask, reinterpret_cast<unsigned long long*>(hist));
+    LSD_LAUNCH_CHECK();
+    return LSD_OK;
+}
+
+// in-place exclusive scan of up to 2^16 uint64 counters (one CTA; every thread owns a run of consecutive entries)
+__global__ void __launch_bounds__(1024)
+field_scan_kernel(uint64_t* __restrict__ a, uint32_t len)
+{
+    __shared__ uint64_t s_part[1024];
+    const uint32_t tid = threadIdx.x;
+    const uint32_t per = (len + 1023u) / 1024u;
+    const uint32_t lo = tid * per, hi = lo + per < len ? lo + per : len;
+    uint64_t sum = 0;
+    for (uint32_t i = lo; i < hi; ++i) sum += a[i];
+    s_part[tid] = sum;
+    __syncthreads();
+    for (uint32_t o = 1; o < 1024; o <<= 1) {
+        const uint64_t t = tid >= o ? s_part[tid - o] : 0;
+        __syncthreads();
+        s_part[tid] += t;
+        __syncthreads();
+    }
+    uint64_t run = s_part[tid] - sum;
+    for (uint32_t i = lo; i < hi; ++i) {
+        const uint64_t v = a[i];
+        a[i] = run;
+        run += v;
+    }
+}
+
+int launch_field_scan(uint64_t* a, int bits, cudaStream_t s)
+{
+    field_scan_kernel<<<1, 1024, 0, s>>>(a, 1u << bits);
+    LSD_LAUNCH_CHECK();
+    return LSD_OK;
+}
+
+// -------------------------------------------------------------------------------------
 // (2) Reference-layout per-tile histograms: h[g*H + d] = #{keys of tile g with digit d},
 //     tile g = keys [g*block, min((g+1)*block, n)).  One warp owns a tile at a time and
 //     walks tiles with a grid stride, so any `block` works (the reference ties it to the

@@ -66,6 +66,8 @@ struct PassArgs {
     uint32_t* vals;             // pairs mode only: the caller's value buffer (travels with `keys`)
     uint32_t* vals_scratch;     // pairs mode only: ping-pong buffer of the values (travels with `scratch`)
     uint32_t key_type;          // lsd_key_type; non-zero only with the typed-key kernels (OnesweepLauncher.launch_typed)
+    uint32_t digit_mask;        // 2^r - 1; narrower for the sub-passes of composite digit widths (honoured by the run-time-shift
+                                // form of onesweep_lpc3_kernel only)
 };
 
 // The key mapping a pass applies when it reads / writes keys: identity unless the keys are typed and this is the first /

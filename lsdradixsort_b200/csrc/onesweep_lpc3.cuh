@@ -40,6 +40,8 @@ onesweep_lpc3_kernel(const PassArgs a)
     constexpr int IN_OFF = (S_::WORDS + 3) & ~3;               // else: a dedicated prefetch buffer behind everything
     static_assert(LBT >= H / 2, "one digit pair per look-back thread");
     const int shift = SHIFT >= 0 ? SHIFT : a.shift;
+    // run-time digits may be narrower than RB bits (sub-passes of the composite digit widths, sort.cu: pass_enqueue_wide)
+    const uint32_t dmask = SHIFT >= 0 ? (uint32_t)(H - 1) : a.digit_mask;
 
     if (a.plan->skip[a.pass]) return;
 
@@ -85,7 +87,7 @@ onesweep_lpc3_kernel(const PassArgs a)
     const uint32_t lane4 = lane << 2;
     auto cell_of = [&](uint32_t key) -> uint32_t {  // byte offset of cell (digit, lane) in the matrix
         if constexpr (SHIFT >= 0) return cell_offset<RB, SHIFT < 0 ? 0 : SHIFT>(key, lane4);
-        else return (((key >> shift) & (uint32_t)(H - 1)) << 7) | lane4;
+        else return (((key >> shift) & dmask) << 7) | lane4;
     };
     uint32_t phase = 0;
     const KeyXform xin = TYPED ? pass_xform_in(a) : KeyXform{0u, 0u};
@@ -250,7 +252,7 @@ onesweep_lpc3_kernel(const PassArgs a)
             if (dt < (uint32_t)H / 2) {
             const uint32_t cnt_lo = s_tot[2 * dt];
             uint32_t cnt_hi = s_tot[2 * dt + 1];
-            if (dt == (uint32_t)H / 2 - 1) cnt_hi -= pads;
+            if (2 * dt + 1 == dmask) cnt_hi -= pads;  // the pads of a ragged tile carry the largest digit in use
             const uint32_t dp_lo = s_dp[2 * dt], dp_hi = s_dp[2 * dt + 1];
             uint32_t ex_lo = 0, ex_hi = 0;
             if (tile == 0) {
@@ -350,12 +352,12 @@ onesweep_lpc3_kernel(const PassArgs a)
             for (int i = 0; i < ITEMS; ++i) {
                 const uint32_t p = i * THREADS + tid;
                 const uint32_t k = s_keys[p];
-                st_key<5>(out + s_gbase[(k >> shift) & (H - 1)] + p, k);
+                st_key<5>(out + s_gbase[(k >> shift) & dmask] + p, k);
             }
         } else {
             for (uint32_t p = tid; p < valid; p += THREADS) {
                 const uint32_t k = s_keys[p];
-                out[s_gbase[(k >> shift) & (H - 1)] + p] = TYPED ? key_from_unsigned(k, xout) : k;
+                out[s_gbase[(k >> shift) & dmask] + p] = TYPED ? key_from_unsigned(k, xout) : k;
             }
         }
         if (warp == 0) LSD_TRACE(12);
@@ -386,12 +388,14 @@ template <int RB, int WARPS, int ITEMS, int MINB, int LB, int CLR, int NOB5, boo
 int onesweep_lpc3_launch(const PassArgs& a, cudaStream_t s)
 {
     if constexpr (RB != 8) return onesweep_lpc3_launch_shift<RB, WARPS, ITEMS, MINB, -1, LB, CLR, NOB5, TYPED, TRACE>(a, s);
-    switch (a.shift) {
+    if (a.digit_mask == 0xFFu) switch (a.shift) {
         case 0: return onesweep_lpc3_launch_shift<RB, WARPS, ITEMS, MINB, 0, LB, CLR, NOB5, TYPED, TRACE>(a, s);
         case 8: return onesweep_lpc3_launch_shift<RB, WARPS, ITEMS, MINB, 8, LB, CLR, NOB5, TYPED, TRACE>(a, s);
         case 16: return onesweep_lpc3_launch_shift<RB, WARPS, ITEMS, MINB, 16, LB, CLR, NOB5, TYPED, TRACE>(a, s);
         case 24: return onesweep_lpc3_launch_shift<RB, WARPS, ITEMS, MINB, 24, LB, CLR, NOB5, TYPED, TRACE>(a, s);
     }
+    // any other shift / a digit narrower than 8 bits: the run-time form (plain keys, no trace)
+    if constexpr (!TYPED && !TRACE) return onesweep_lpc3_launch_shift<RB, WARPS, ITEMS, MINB, -1, LB, CLR, NOB5, false, false>(a, s);
     return LSD_ERR_INVALID_VALUE;
 }
 

@@ -122,7 +122,8 @@ static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 int make_layout(uint64_t n, int r, int block, const lsd_sort_options* opt, SortLayout* L, bool pairs)
 {
-    if (!valid_radix(r)) return LSD_ERR_INVALID_VALUE;
+    if (!accepted_radix(r)) return LSD_ERR_INVALID_VALUE;
+    r = exec_radix(r);  // composite digit widths (11, 16, ...): the full sort runs the 8-bit schedule, same result
     if (block < 0 || block > 1024) return LSD_ERR_INVALID_VALUE;
     if (n > (1ull << 32)) return LSD_ERR_UNSUPPORTED;  // key positions are 32-bit (n = 2^32 included: the last position is 2^32 - 1)
     const uint32_t variant = opt ? opt->variant : 0u;
@@ -168,6 +169,7 @@ int sort_enqueue(uint32_t* keys, uint32_t* scratch, uint64_t n, int r, int block
     SortLayout L;
     const int st = make_layout(n, r, block, opt, &L, pairs);
     if (st != LSD_OK) return st;
+    r = exec_radix(r);
     if (launches) *launches = 0;
     if (n == 0) return LSD_OK;
     if (!keys || !scratch || !ws) return LSD_ERR_INVALID_VALUE;
@@ -220,6 +222,7 @@ int sort_enqueue(uint32_t* keys, uint32_t* scratch, uint64_t n, int r, int block
             a.vals = vals;
             a.vals_scratch = vals_scratch;
             a.key_type = key_type;
+            a.digit_mask = (uint32_t)L.H - 1u;
             rc = pass_fn(*L.k, pairs, key_type != 0u)(a, s);
             if (rc != LSD_OK) return rc;
             ++nl;
@@ -332,9 +335,133 @@ int pass_enqueue(const uint32_t* in, uint32_t* out, uint64_t n, int r, int bit_g
         a.vals = nullptr;
         a.vals_scratch = nullptr;
         a.key_type = 0;
+        a.digit_mask = (uint32_t)L.H - 1u;
         rc = peer ? L.k->launch_peer(a, s) : L.k->launch(a, s);
         if (rc != LSD_OK) return rc;
         lb += (size_t)a.tiles * L.H;
+    }
+    return LSD_OK;
+}
+
+// -------------------------------------------------------------------------------------
+// single pass on a COMPOSITE digit width (r in 3..16 other than 4 and 8): digit `bit_group` is bits
+// [bit_group*r, min(32, (bit_group+1)*r)).  A stable counting-sort pass on a w-bit digit equals a stable pass on its
+// low 8 bits followed by a stable pass on the remaining w-8 bits (the LSD argument applied inside the digit), so it
+// runs as one or two sub-passes of the 8-bit kernel in its run-time (shift, mask) form; two sub-passes go through a
+// temporary key array in the workspace.  hist_out gets the 2^r bucket starts of the whole digit.
+// Workspace: [r = 8 sort layout][2^16 uint64 field histogram][n keys of temporary space].
+// -------------------------------------------------------------------------------------
+struct WideLayout {
+    SortLayout L;
+    size_t off_field, off_tmp, total_bytes;
+};
+
+static int make_wide_layout(uint64_t n, WideLayout* W)
+{
+    const int st = make_layout(n, 8, 0, nullptr, &W->L);
+    if (st != LSD_OK) return st;
+    size_t off = align_up(W->L.total_bytes, 256);
+    W->off_field = off;  off = align_up(off + (sizeof(uint64_t) << 16), 256);
+    W->off_tmp = off;    off = align_up(off + sizeof(uint32_t) * (size_t)n, 256);
+    W->total_bytes = off;
+    return LSD_OK;
+}
+
+size_t wide_pass_workspace_bytes(uint64_t n)
+{
+    WideLayout W;
+    return make_wide_layout(n, &W) == LSD_OK ? W.total_bytes : 0;
+}
+
+static int sub_pass_enqueue(const uint32_t* in, uint32_t* out, uint64_t n, int shift, int bits, const SortLayout& L, char* w,
+                            cudaStream_t s)
+{
+    SortPlan* plan = reinterpret_cast<SortPlan*>(w + L.off_plan);
+    uint64_t* hist = reinterpret_cast<uint64_t*>(w + L.off_hist);
+    uint64_t* bases = reinterpret_cast<uint64_t*>(w + L.off_bases);
+    uint32_t* tickets = reinterpret_cast<uint32_t*>(w + L.off_tickets);
+    uint32_t* lookback = reinterpret_cast<uint32_t*>(w + L.off_lookback);
+    LSD_CUDA_TRY(cudaMemsetAsync(w, 0, L.off_lookback + sizeof(uint32_t) * (size_t)L.total_tiles * L.H, s));
+    int rc = launch_field_histogram(in, n, shift, bits, hist, s);  // row 0 of the [4][256] area; bins >= 2^bits stay zero
+    if (rc != LSD_OK) return rc;
+    single_pass_plan_kernel<<<1, kPlanThreads, 0, s>>>(hist, bases, plan, nullptr, 0, L.H, 0, nullptr);
+    LSD_LAUNCH_CHECK();
+    uint32_t* lb = lookback;
+    for (uint64_t q = 0; q < L.portions; ++q) {
+        const uint64_t pbase = q * (uint64_t)L.portion_keys;
+        const uint32_t pkeys = (uint32_t)std::min<uint64_t>(L.portion_keys, n - pbase);
+        PassArgs a;
+        a.keys = const_cast<uint32_t*>(in);
+        a.scratch = out;
+        a.plan = plan;
+        a.bases_in = bases + (size_t)(q & 1) * L.H;
+        a.bases_out = (q + 1 < L.portions) ? bases + (size_t)((q + 1) & 1) * L.H : nullptr;
+        a.lookback = lb;
+        a.ticket = tickets + q;
+        a.portion_base = pbase;
+        a.portion_keys = pkeys;
+        a.tiles = (pkeys + L.k->tile - 1) / L.k->tile;
+        a.pass = 0;
+        a.shift = shift;
+        a.trace = nullptr;
+        a.dst_ptrs = nullptr;
+        a.dst_seg = nullptr;
+        a.vals = nullptr;
+        a.vals_scratch = nullptr;
+        a.key_type = 0;
+        a.digit_mask = (1u << bits) - 1u;
+        rc = L.k->launch(a, s);
+        if (rc != LSD_OK) return rc;
+        lb += (size_t)a.tiles * L.H;
+    }
+    return LSD_OK;
+}
+
+int pass_enqueue_wide(const uint32_t* in, uint32_t* out, uint64_t n, int r, int bit_group, void* ws, size_t ws_bytes,
+                      uint64_t* hist_out, cudaStream_t s)
+{
+    if (!composite_radix(r)) return LSD_ERR_INVALID_VALUE;
+    if (bit_group < 0 || bit_group >= digit_count(r)) return LSD_ERR_INVALID_VALUE;
+    WideLayout W;
+    const int st = make_wide_layout(n, &W);
+    if (st != LSD_OK) return st;
+    if (n == 0) {
+        if (hist_out) LSD_CUDA_TRY(cudaMemsetAsync(hist_out, 0, sizeof(uint64_t) << r, s));
+        return LSD_OK;
+    }
+    if (!in || !out || !ws) return LSD_ERR_INVALID_VALUE;
+    if (ws_bytes < W.total_bytes) return LSD_ERR_WORKSPACE_TOO_SMALL;
+    if (!aligned_to(in, 16) || !aligned_to(out, 16) || !aligned_to(ws, 256)) return LSD_ERR_ALIGNMENT;
+    char* w = static_cast<char*>(ws);
+    const int shift = bit_group * r;
+    const int width = std::min(r, 32 - shift);
+    int rc = LSD_OK;
+    if (hist_out) {  // bucket starts of the whole digit; entries above 2^width (a narrower top digit) equal n
+        uint64_t* field = reinterpret_cast<uint64_t*>(w + W.off_field);
+        rc = launch_field_histogram(in, n, shift, width, field, s);
+        if (rc != LSD_OK) return rc;
+        if (width < r) LSD_CUDA_TRY(cudaMemsetAsync(field + ((size_t)1 << width), 0, (sizeof(uint64_t) << r) - (sizeof(uint64_t) << width), s));
+        rc = launch_field_scan(field, r, s);
+        if (rc != LSD_OK) return rc;
+        LSD_CUDA_TRY(cudaMemcpyAsync(hist_out, field, sizeof(uint64_t) << r, cudaMemcpyDeviceToDevice, s));
+    }
+    if (width <= 8) return sub_pass_enqueue(in, out, n, shift, width, W.L, w, s);
+    uint32_t* tmp = reinterpret_cast<uint32_t*>(w + W.off_tmp);
+    rc = sub_pass_enqueue(in, tmp, n, shift, 8, W.L, w, s);
+    if (rc != LSD_OK) return rc;
+    return sub_pass_enqueue(tmp, out, n, shift + 8, width - 8, W.L, w, s);
+}
+
+// [digit_count(r)][2^r] uint64 histograms for a composite digit width: one read of the keys per digit
+int launch_digit_histograms_wide(const uint32_t* keys, uint64_t n, int r, uint64_t* hist, cudaStream_t s)
+{
+    if (!composite_radix(r)) return LSD_ERR_INVALID_VALUE;
+    const int digits = digit_count(r);
+    LSD_CUDA_TRY(cudaMemsetAsync(hist, 0, (sizeof(uint64_t) << r) * digits, s));
+    for (int i = 0; i < digits; ++i) {
+        const int shift = i * r;
+        const int rc = launch_field_histogram(keys, n, shift, std::min(r, 32 - shift), hist + ((size_t)i << r), s);
+        if (rc != LSD_OK) return rc;
     }
     return LSD_OK;
 }

@@ -31,4 +31,14 @@ int pass_enqueue(const uint32_t* in, uint32_t* out, uint64_t n, int r, int bit_g
                  size_t ws_bytes, uint64_t* hist_out, cudaStream_t s, const uint64_t* dst_ptrs = nullptr,
                  const uint32_t* dst_seg = nullptr, const uint32_t* abort_flag = nullptr);
 
+// Composite digit widths (r in 3..16 other than 4, 8): one pass as sub-passes of the 8-bit kernel; per-digit histograms.
+size_t wide_pass_workspace_bytes(uint64_t n);
+int pass_enqueue_wide(const uint32_t* in, uint32_t* out, uint64_t n, int r, int bit_group, void* ws, size_t ws_bytes,
+                      uint64_t* hist_out, cudaStream_t s);
+int launch_digit_histograms_wide(const uint32_t* keys, uint64_t n, int r, uint64_t* hist, cudaStream_t s);
+
+// 64-bit keys (keys64.cu): split into word arrays, two key-value sorts, merge.
+size_t sort64_workspace_bytes(uint64_t n);
+int sort64_enqueue(uint64_t* keys, uint64_t* scratch, uint64_t n, uint32_t key_type, void* ws, size_t ws_bytes, cudaStream_t s);
+
 }  // namespace lsd

@@ -248,3 +248,60 @@ ORACLE_API int lsd_oracle_tiled_pass(const uint32_t *in, uint32_t *out, int64_t 
     free(global_off);
     return 0;
 }
+
+/*
+ * LSDRadixSortPass (LSDRadixSort.cu:25-54) on an arbitrary bit field [shift, shift + width) of the key instead
+ * of GET_R_BITS(val, r, bit_group): the digit of the composite widths (r = 11: fields 0/11, 11/11, 22/10; any
+ * r: field bit_group*r / min(r, 32 - bit_group*r)).  Same three sweeps, no copy-back; `histogram` (2^width
+ * words) is left holding the bucket START offsets.  Checker for lsd_sort_pass with composite r.
+ */
+ORACLE_API void lsd_oracle_sort_pass_field(const uint32_t *in, uint32_t *out, int64_t count, uint64_t *histogram,
+                                           int shift, int width)
+{
+    const size_t buckets = (size_t)1 << width;
+    const uint32_t mask = (uint32_t)(buckets - 1);
+    memset(histogram, 0, buckets * sizeof(uint64_t));
+    for (int64_t i = 0; i < count; ++i)
+        histogram[(in[i] >> shift) & mask] += 1u;
+    uint64_t running = 0;
+    for (size_t b = 0; b < buckets; ++b) {
+        running += histogram[b];
+        histogram[b] = running;
+    }
+    for (int64_t i = count; i-- > 0;) {
+        const uint32_t key = in[i];
+        out[--histogram[(key >> shift) & mask]] = key;
+    }
+}
+
+/*
+ * LSDRadixSort (LSDRadixSort.cu:62-69) widened to 64-bit keys: 64/r passes of LSDRadixSortPass (:25-54), least
+ * significant digit first, with the digit taken from a 64-bit word.  The reference sorts uint32 only; this is
+ * the same loop and the same pass with the key type changed.  Checker for lsd_sort64.  `histogram`: 2^r words.
+ * Returns -1 unless r divides 64 and r <= 16.
+ */
+ORACLE_API int lsd_oracle_sort64(uint64_t *in, uint64_t *out, int64_t count, uint64_t *histogram, int r)
+{
+    if (r <= 0 || r > 16 || (64 % r) != 0)
+        return -1;
+    const size_t buckets = (size_t)1 << r;
+    const uint64_t mask = (uint64_t)buckets - 1u;
+    for (int g = 0; g < 64 / r; ++g) {
+        const int shift = g * r;
+        memset(histogram, 0, buckets * sizeof(uint64_t));
+        for (int64_t i = 0; i < count; ++i)
+            histogram[(in[i] >> shift) & mask] += 1u;
+        uint64_t running = 0;
+        for (size_t b = 0; b < buckets; ++b) {
+            running += histogram[b];
+            histogram[b] = running;
+        }
+        for (int64_t i = count; i-- > 0;) {
+            const uint64_t key = in[i];
+            out[--histogram[(key >> shift) & mask]] = key;
+        }
+        if (count > 0)
+            memcpy(in, out, (size_t)count * sizeof(uint64_t));
+    }
+    return 0;
+}

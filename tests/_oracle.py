@@ -51,6 +51,10 @@ def oracle() -> C.CDLL:
         l.lsd_oracle_digit_histograms.argtypes = [_u32p, C.c_int64, C.c_int, _u64p]
         l.lsd_oracle_tiled_pass.restype = C.c_int
         l.lsd_oracle_tiled_pass.argtypes = [_u32p, _u32p, C.c_int64, C.c_int, C.c_int, C.c_int]
+        l.lsd_oracle_sort_pass_field.restype = None
+        l.lsd_oracle_sort_pass_field.argtypes = [_u32p, _u32p, C.c_int64, _u64p, C.c_int, C.c_int]
+        l.lsd_oracle_sort64.restype = C.c_int
+        l.lsd_oracle_sort64.argtypes = [_u64p, _u64p, C.c_int64, _u64p, C.c_int]
         _oracle = l
     return _oracle
 
@@ -154,3 +158,54 @@ def sort_typed(bits: np.ndarray, key_type: str, r: int = 8) -> np.ndarray:
 def sort_pairs_typed(bits: np.ndarray, vals: np.ndarray, key_type: str, r: int = 8):
     k, v = sort_pairs(to_unsigned(bits, key_type), vals, r)
     return from_unsigned(k, key_type), v
+
+
+# ---- composite digit widths and 64-bit keys --------------------------------------------------------
+def digit_field(r: int, bit_group: int):
+    """(shift, width) of digit `bit_group` at width r: bits [bit_group*r, min(32, (bit_group+1)*r))."""
+    shift = bit_group * r
+    return shift, min(r, 32 - shift)
+
+
+def sort_pass_field(keys: np.ndarray, shift: int, width: int):
+    """(out, bucket starts) of the reference's pass on the bit field [shift, shift+width)."""
+    a = np.ascontiguousarray(keys, dtype=np.uint32)
+    out = np.empty_like(a)
+    hist = np.zeros(1 << width, dtype=np.uint64)
+    oracle().lsd_oracle_sort_pass_field(a, out, a.size, hist, shift, width)
+    return out, hist
+
+
+def field_histogram(keys: np.ndarray, shift: int, width: int) -> np.ndarray:
+    a = np.ascontiguousarray(keys, dtype=np.uint32)
+    return np.bincount((a >> np.uint32(shift)) & np.uint32((1 << width) - 1), minlength=1 << width).astype(np.uint64)
+
+
+def to_unsigned64(bits: np.ndarray, key_type: str) -> np.ndarray:
+    b = np.ascontiguousarray(bits).view(np.uint64)
+    if key_type == "u64":
+        return b.copy()
+    top = np.uint64(1 << 63)
+    if key_type == "i64":
+        return b ^ top
+    assert key_type == "f64"
+    return np.where(b >> np.uint64(63), ~b, b ^ top).astype(np.uint64)
+
+
+def from_unsigned64(u: np.ndarray, key_type: str) -> np.ndarray:
+    top = np.uint64(1 << 63)
+    if key_type == "u64":
+        return u.copy()
+    if key_type == "i64":
+        return u ^ top
+    return np.where(u >> np.uint64(63), u ^ top, ~u).astype(np.uint64)
+
+
+def sort64(bits: np.ndarray, key_type: str = "u64", r: int = 8) -> np.ndarray:
+    """Sorted 64-bit patterns in `key_type` order: the reference's LSD loop on 64-bit words (lsd_oracle_sort64)."""
+    a = to_unsigned64(bits, key_type)
+    out = np.empty_like(a)
+    hist = np.zeros(1 << r, dtype=np.uint64)
+    rc = oracle().lsd_oracle_sort64(a, out, a.size, hist, r)
+    assert rc == 0
+    return from_unsigned64(out, key_type)

@@ -60,11 +60,17 @@ def test_size_queries_need_no_gpu():
         assert 0 < a < b
         # never more scratch than the 3*G*H words the reference needs at B=256 (.cu:919-929) for large inputs
         assert lib.lsd_sort_workspace_bytes(1 << 28, r, 256) <= 3 * ((1 << 28) // 256) * (1 << r) * 4 + (1 << 20)
-    assert lib.lsd_sort_workspace_bytes(1 << 20, 3, 0) == 0
+    assert lib.lsd_sort_workspace_bytes(1 << 20, 0, 0) == 0
+    assert lib.lsd_sort_workspace_bytes(1 << 20, 17, 0) == 0
+    # composite digit widths (every r in 3..16 other than 4 and 8): the 8-bit layout plus the temporary key
+    # array and the 2^16-bin histogram of lsd_sort_pass's sub-passes
+    for r in (3, 11, 16):
+        assert lib.lsd_sort_workspace_bytes(1 << 20, r, 0) >= lib.lsd_sort_workspace_bytes(1 << 20, 8, 0) + (4 << 20) + (8 << 16)
+    assert 0 < lib.lsd_sort64_workspace_bytes(0) <= lib.lsd_sort64_workspace_bytes(1 << 20)
     assert lib.lsd_sort_workspace_bytes(1 << 20, 8, 2048) == 0
 
 
-@pytest.mark.parametrize("r,block", [(0, 256), (3, 256), (16, 256), (8, -1), (8, 4096)])
+@pytest.mark.parametrize("r,block", [(0, 256), (-8, 256), (17, 256), (32, 256), (8, -1), (8, 4096)])
 def test_sort_rejects_bad_parameters_without_cuda(r, block):
     lib = N.lib()
     st = lib.lsd_sort(0x1000, 0x2000, 1024, r, block, 0x3000, 1 << 30, None)
@@ -90,7 +96,13 @@ def test_histogram_and_scan_argument_validation():
     assert lib.lsd_build_histogram(0x1000, 1024, 8, -1, 256, 0x2000, None) == N.LSD_ERR_INVALID_VALUE
     assert lib.lsd_build_histogram(0x1000, 1024, 8, 0, 0, 0x2000, None) == N.LSD_ERR_INVALID_VALUE
     assert lib.lsd_build_histogram(None, 0, 8, 0, 256, None, None) == N.LSD_OK
-    assert lib.lsd_digit_histograms(0x1000, 16, 5, 0x2000, None) == N.LSD_ERR_INVALID_VALUE
+    assert lib.lsd_digit_histograms(0x1000, 16, 17, 0x2000, None) == N.LSD_ERR_INVALID_VALUE
+    assert lib.lsd_sort_pass(0x1000, 0x2000, 16, 11, 3, 0, 0x3000, 1 << 30, None, None) == N.LSD_ERR_INVALID_VALUE  # r = 11 has 3 digits
+    assert lib.lsd_sort_pass(0x1000, 0x2000, 16, 16, 0, 0, 0x3000, 16, None, None) == N.LSD_ERR_WORKSPACE_TOO_SMALL
+    assert lib.lsd_sort64(0x1000, 0x2000, 16, 0, 0x3000, 1 << 30, None) == N.LSD_ERR_INVALID_VALUE  # a 32-bit key type
+    assert lib.lsd_sort64(0x1000, 0x2008, 16, 3, 0x3000, 1 << 30, None) == N.LSD_ERR_ALIGNMENT
+    assert lib.lsd_sort64(0x1000, 0x2000, 16, 3, 0x3000, 16, None) == N.LSD_ERR_WORKSPACE_TOO_SMALL
+    assert lib.lsd_sort64(None, None, 0, 3, None, 0, None) == N.LSD_OK
     assert lib.lsd_prefix_sum(None, 0, 256, None, 0, None) == N.LSD_OK
     assert lib.lsd_prefix_sum(0x1000, 16, 4096, 0x2000, 1 << 20, None) == N.LSD_ERR_INVALID_VALUE
     assert lib.lsd_prefix_sum(0x1004, 16, 256, 0x2000, 1 << 20, None) == N.LSD_ERR_ALIGNMENT

@@ -47,12 +47,12 @@ def test_pairs_abi_validation_without_cuda():
     lib = N.lib()
     big = 1 << 30
     assert lib.lsd_sort_pairs(None, None, None, None, 0, 8, 0, None, 0, None, None) == N.LSD_OK
-    assert lib.lsd_sort_pairs(None, None, None, None, 0, 3, 0, None, 0, None, None) == N.LSD_ERR_INVALID_VALUE
+    assert lib.lsd_sort_pairs(None, None, None, None, 0, 17, 0, None, 0, None, None) == N.LSD_ERR_INVALID_VALUE
     assert lib.lsd_sort_pairs(0x1000, None, 0x3000, 0x4000, 16, 8, 0, 0x5000, big, None, None) == N.LSD_ERR_INVALID_VALUE
     assert lib.lsd_sort_pairs(0x1000, 0x2000, 0x3000, None, 16, 8, 0, 0x5000, big, None, None) == N.LSD_ERR_INVALID_VALUE
     assert lib.lsd_sort_pairs(0x1000, 0x2004, 0x3000, 0x4000, 16, 8, 0, 0x5000, big, None, None) == N.LSD_ERR_ALIGNMENT
     assert lib.lsd_sort_pairs(0x1000, 0x2000, 0x3000, 0x4000, 16, 8, 0, 0x5000, 16, None, None) == N.LSD_ERR_WORKSPACE_TOO_SMALL
-    assert lib.lsd_sort_pairs(0x1000, 0x2000, 0x3000, 0x4000, 16, 5, 0, 0x5000, big, None, None) == N.LSD_ERR_INVALID_VALUE
+    assert lib.lsd_sort_pairs(0x1000, 0x2000, 0x3000, 0x4000, 16, 0, 0, 0x5000, big, None, None) == N.LSD_ERR_INVALID_VALUE
     for r in (1, 2, 4, 8):
         assert lib.lsd_sort_pairs_workspace_bytes(1 << 20, r, 0, None) > 0
         for block in (128, 256, 512, 1024):
