@@ -23,6 +23,20 @@ __device__ __forceinline__ void mbar_arrive_release(uint64_t* bar)
     asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// bulk (TMA) store shared -> global, completion tracked by the issuing thread's bulk async-group
+__device__ __forceinline__ void tma_bulk_s2g(void* dst_gmem, const void* src_smem, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes)
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void tma_bulk_wait_read_all()
+{
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
+// CLR: 8 = as 0, and the look-back records are PUBLISHED by TMA bulk stores from a shared-memory copy of the record (they
+//      do not queue behind the copy-out stores of the three resident CTAs in the LSU pipe)
 // CLR: 0 = matrix cleared with 128-bit stores, 1 = st.bulk, 2 = TMA copy of a zero page (keeps the clear off the LSU pipe)
 // NOB5: 1 = no CTA-wide barrier at the end of a tile: the next ticket is handed over through a second mbarrier
 // TYPED: i32 / f32 keys are mapped to unsigned order when the first executed pass reads them and back when the last one writes
@@ -39,6 +53,8 @@ onesweep_lpc3_kernel(const PassArgs a)
     constexpr bool ALIAS = S_::OFF_DP - S_::OFF_MAT >= TILE;  // the dead matrix (+ tile counts) can hold the incoming tile
     constexpr int IN_OFF = (S_::WORDS + 3) & ~3;               // else: a dedicated prefetch buffer behind everything
     static_assert(LBT >= H / 2, "one digit pair per look-back thread");
+    constexpr bool PUB = CLR == 8;
+    static_assert(!PUB || (H == 256 && S_::OFF_HEADS + H + 4 - S_::OFF_DST >= 4 * H), "record copies live in the unused peer-scatter area");
     const int shift = SHIFT >= 0 ? SHIFT : a.shift;
     // run-time digits may be narrower than RB bits (sub-passes of the composite digit widths, sort.cu: pass_enqueue_wide)
     const uint32_t dmask = SHIFT >= 0 ? (uint32_t)(H - 1) : a.digit_mask;
@@ -55,6 +71,7 @@ onesweep_lpc3_kernel(const PassArgs a)
     uint32_t* s_misc = smem + S_::OFF_MISC;
     uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_misc + 34);
     uint64_t* s_bar2 = reinterpret_cast<uint64_t*>(s_misc + 36);  // "next ticket is in s_misc[32]" (NOB5)
+    uint32_t* s_rec = smem + S_::OFF_DST;  // PUB: [tile parity][LOCAL, INCLUSIVE][H] record copies, the source of the bulk stores
 
     const uint32_t tid = threadIdx.x;
     const uint32_t lane = tid & 31u;
@@ -255,10 +272,21 @@ onesweep_lpc3_kernel(const PassArgs a)
             if (2 * dt + 1 == dmask) cnt_hi -= pads;  // the pads of a ragged tile carry the largest digit in use
             const uint32_t dp_lo = s_dp[2 * dt], dp_hi = s_dp[2 * dt + 1];
             uint32_t ex_lo = 0, ex_hi = 0;
+            [[maybe_unused]] uint32_t* rec = s_rec + (tile & 1u) * (2 * H);
+            if constexpr (PUB) {
+                // the bulk stores this thread issued for the previous tile have read their source (the same-parity copy is
+                // rewritten one tile later, behind that tile's CTA-wide barriers)
+                if (lane == 0) tma_bulk_wait_read_all();
+                const uint32_t flag = tile == 0 ? kLbGlobal : kLbLocal;
+                *reinterpret_cast<uint2*>(rec + 2 * dt) = make_uint2(flag | cnt_lo, flag | cnt_hi);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                named_bar_sync(13, H / 2);
+                if (dt == 0) tma_bulk_s2g(lb_row, rec, H * 4);
+            }
             if (tile == 0) {
-                st_relaxed_gpu_v2(lb_row + 2 * dt, kLbGlobal | cnt_lo, kLbGlobal | cnt_hi);
+                if constexpr (!PUB) st_relaxed_gpu_v2(lb_row + 2 * dt, kLbGlobal | cnt_lo, kLbGlobal | cnt_hi);
             } else {
-                st_relaxed_gpu_v2(lb_row + 2 * dt, kLbLocal | cnt_lo, kLbLocal | cnt_hi);
+                if constexpr (!PUB) st_relaxed_gpu_v2(lb_row + 2 * dt, kLbLocal | cnt_lo, kLbLocal | cnt_hi);
                 const uint32_t* p = lb_row - H + 2 * dt;
                 uint32_t remaining = tile;
                 bool done = false;
@@ -305,7 +333,14 @@ onesweep_lpc3_kernel(const PassArgs a)
                         a.trace[(size_t)tile * 16 + 15] = (unsigned long long)dbg_wait;  // sum over rounds: loads issued -> all landed
                         a.trace[(size_t)tile * 16 + 7] = (unsigned long long)dbg_proc;   // sum over rounds: landed -> round done
                     }
-                st_relaxed_gpu_v2(lb_row + 2 * dt, kLbGlobal | (ex_lo + cnt_lo), kLbGlobal | (ex_hi + cnt_hi));
+                if constexpr (PUB) {  // one 256-byte bulk store per look-back warp (64 digits), when its slowest lane is done
+                    *reinterpret_cast<uint2*>(rec + H + 2 * dt) = make_uint2(kLbGlobal | (ex_lo + cnt_lo), kLbGlobal | (ex_hi + cnt_hi));
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) tma_bulk_s2g(lb_row + 2 * dt, rec + H + 2 * dt, 256);
+                } else {
+                    st_relaxed_gpu_v2(lb_row + 2 * dt, kLbGlobal | (ex_lo + cnt_lo), kLbGlobal | (ex_hi + cnt_hi));
+                }
             }
             const uint64_t b_lo = a.bases_in[2 * dt], b_hi = a.bases_in[2 * dt + 1];
             s_gbase[2 * dt] = (uint32_t)b_lo + ex_lo - dp_lo;

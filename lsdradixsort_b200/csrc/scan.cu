@@ -667,8 +667,14 @@ scan_cluster_kernel(uint32_t* __restrict__ a, uint64_t n, ScanWorkspace* __restr
 // LSD_SCAN_CLUSTER=1 selects scan_cluster_kernel (one look-back record per cluster of 8 tiles).  Measured on B200 it does not
 // beat scan_tma_kernel (0.528 vs 0.512 ms at 2^28): the two cluster barriers at the start (all 8 CTAs must have started before
 // their shared memory may be written) and the wait for the slowest of 8 tile loads cost what the shorter look-back saves.
-static const bool g_scan_no_cluster = [] { const char* e = getenv("LSD_SCAN_CLUSTER"); return !(e && e[0] == '1'); }();
-static const bool g_scan_register_path = [] { const char* e = getenv("LSD_SCAN_REGISTER_PATH"); return e && e[0] == '1'; }();
+// The product library reads no environment: the switches exist in the tuning build (make TUNING=1) only.
+#ifdef LSD_TUNING_VARIANTS
+static bool scan_env(const char* name) { const char* e = getenv(name); return e && e[0] == '1'; }
+#else
+static constexpr bool scan_env(const char*) { return false; }
+#endif
+static const bool g_scan_no_cluster = !scan_env("LSD_SCAN_CLUSTER");
+static const bool g_scan_register_path = scan_env("LSD_SCAN_REGISTER_PATH");
 
 static int scan_threads_for(int block)
 {
@@ -679,8 +685,8 @@ static int scan_threads_for(int block)
 }
 
 // LSD_SCAN_TRACE=1 (tuning aid): 8 uint32 phase clocks per tile are written after the tile states
-static const bool g_scan_l2 = [] { const char* e = getenv("LSD_SCAN_L2"); return e && e[0] == '1'; }();
-static const bool g_scan_trace = [] { const char* e = getenv("LSD_SCAN_TRACE"); return e && e[0] == '1'; }();
+static const bool g_scan_l2 = scan_env("LSD_SCAN_L2");
+static const bool g_scan_trace = scan_env("LSD_SCAN_TRACE");
 
 size_t scan_workspace_bytes(uint64_t n, int block)
 {
