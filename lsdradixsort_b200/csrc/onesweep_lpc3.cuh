@@ -54,6 +54,7 @@ onesweep_lpc3_kernel(const PassArgs a)
     constexpr int IN_OFF = (S_::WORDS + 3) & ~3;               // else: a dedicated prefetch buffer behind everything
     static_assert(LBT >= H / 2, "one digit pair per look-back thread");
     constexpr bool PUB = CLR == 8;
+    constexpr bool WALK2 = CLR == 9;  // pipelined look-back walk: next window in flight, whole-window fast path
     static_assert(!PUB || (H == 256 && S_::OFF_HEADS + H + 4 - S_::OFF_DST >= 4 * H), "record copies live in the unused peer-scatter area");
     const int shift = SHIFT >= 0 ? SHIFT : a.shift;
     // run-time digits may be narrower than RB bits (sub-passes of the composite digit widths, sort.cu: pass_enqueue_wide)
@@ -292,6 +293,56 @@ onesweep_lpc3_kernel(const PassArgs a)
                 bool done = false;
                 [[maybe_unused]] uint32_t dbg_rounds = 0, dbg_hops = 0;
                 [[maybe_unused]] long long dbg_wait = 0, dbg_proc = 0;
+                if constexpr (WALK2) {
+                    // A round of the plain walk costs ~1.2 K cycles, most of it the dependent consume chain of the window
+                    // issued among ~27 resident warps, and the walk takes (hops / LB) rounds.  Here the NEXT window's loads
+                    // are in flight while this one is consumed, and a window whose LB records are all LOCAL is consumed
+                    // by two adds (LB = 4 LOCAL flags sum to 0 mod 2^32).
+                    static_assert(LB == 4, "the flag bits of four LOCAL words cancel");
+                    uint2 cur[LB], nxt[LB];
+#pragma unroll
+                    for (int k = 0; k < LB; ++k)
+                        cur[k] = (uint32_t)k < remaining ? ld_relaxed_gpu_v2(p - (size_t)k * H) : make_uint2(0u, 0u);
+                    while (!done) {
+                        if constexpr (TRACE) ++dbg_rounds;
+                        const bool more = remaining > (uint32_t)LB;
+                        if (more) {
+#pragma unroll
+                            for (int k = 0; k < LB; ++k)
+                                nxt[k] = (uint32_t)(LB + k) < remaining ? ld_relaxed_gpu_v2(p - (size_t)(LB + k) * H) : make_uint2(0u, 0u);
+                        }
+                        const uint32_t lo = min(min(cur[0].x, cur[1].x), min(cur[2].x, cur[3].x));
+                        const uint32_t any = cur[0].x | cur[1].x | cur[2].x | cur[3].x;
+                        if (lo != 0u && (any & kLbGlobal) == 0u) {  // four LOCAL records (then `more` holds: tile 0 is GLOBAL)
+                            ex_lo += cur[0].x + cur[1].x + cur[2].x + cur[3].x;
+                            ex_hi += cur[0].y + cur[1].y + cur[2].y + cur[3].y;
+                            p -= (size_t)LB * H;
+                            remaining -= (uint32_t)LB;
+                            if constexpr (TRACE) dbg_hops += LB;
+#pragma unroll
+                            for (int k = 0; k < LB; ++k) cur[k] = nxt[k];
+                            continue;
+                        }
+                        uint32_t consumed = 0;
+#pragma unroll
+                        for (int k = 0; k < LB; ++k) {
+                            if (!done && consumed == (uint32_t)k && cur[k].x != 0) {
+                                ex_lo += cur[k].x & kLbValueMask;
+                                ex_hi += cur[k].y & kLbValueMask;
+                                ++consumed;
+                                if (cur[k].x & kLbGlobal) done = true;
+                            }
+                        }
+                        if constexpr (TRACE) dbg_hops += consumed;
+                        if (!done) {  // the window moved by less than LB records: fetch it again from where the walk stands
+                            p -= (size_t)consumed * H;
+                            remaining -= consumed;
+#pragma unroll
+                            for (int k = 0; k < LB; ++k)
+                                cur[k] = (uint32_t)k < remaining ? ld_relaxed_gpu_v2(p - (size_t)k * H) : make_uint2(0u, 0u);
+                        }
+                    }
+                }
                 while (!done) {
                     if constexpr (TRACE) ++dbg_rounds;
                     [[maybe_unused]] const long long t_a = TRACE ? clock64() : 0;

@@ -15,10 +15,13 @@ static const OnesweepLauncher kPart[] = {
     make_lpc3_launcher<8, 9, 29, 3, 4, 0, 1, 1>(),  // 0: default -- persistent LPC32 pass, next tile prefetched into the dead counter matrix, ticket hand-over by mbarrier (= variant 75); peer-scatter / key-value / typed-key passes on onesweep_lpc32_kernel (= variant 68)
     make_launcher<8, 256, 16, kMatchBallot, true>(),   // 1: warp multisplit (8 ballots + popc), every form but peer-scatter
     make_lpc32_launcher<8, 9, 29, 3>(),          // 2: non-persistent LPC32 pass, plain keys only
-    make_lpc3_launcher<8, 9, 29, 3, 4, 8, 1>(),  // 3: EXPERIMENT: 0 with the look-back records published by TMA bulk stores
-    make_lpc3_launcher<8, 9, 29, 3, 4, 8, 1, 0, true>(),  // 4: 3 with the per-tile phase trace
-    make_lpc3_launcher<8, 9, 29, 3, 4, 0, 1, 0, true>(),  // 5: 0 with the per-tile phase trace
 #ifdef LSD_TUNING_VARIANTS
+    // round-2 look-back experiments on the default (profiles/r02_lookback_experiments.txt); A0..A5 = variants 3..8
+    make_lpc3_launcher<8, 9, 29, 3, 4, 9, 1>(),  // A0: 0 with the pipelined look-back walk (next window in flight, whole-window fast path)
+    make_lpc3_launcher<8, 9, 29, 3, 4, 9, 1, 0, true>(),  // A1: A0 with the per-tile phase trace
+    make_lpc3_launcher<8, 9, 29, 3, 4, 0, 1, 0, true>(),  // A2: 0 with the per-tile phase trace
+    make_lpc3_launcher<8, 9, 29, 3, 4, 8, 1>(),  // A3: 0 with the look-back records published by TMA bulk stores
+    make_lpc3_launcher<8, 9, 29, 3, 4, 8, 1, 0, true>(),  // A4: A3 with the per-tile phase trace
     make_lpc4_launcher<8, 9, 29, 3, 8, 0, 1>(),  // 3: persistent pass with two rank chains, look-back window 8 (round 2: no gain, see profiles/r02_wide_pass_study.txt)
     make_lpc4_launcher<8, 9, 29, 3, 4, 0, 1>(),  // 4: two rank chains, window 4
     make_lpc4_launcher<8, 9, 29, 3, 8, 0, 1, 0, true>(),  // 5: 3 with the per-tile phase trace
