@@ -332,6 +332,18 @@ def run_ours(args):
     L.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     distributed = world > 1
+    numa_note = None
+    if distributed:
+        # every rank copies 2 x 4 x n_local bytes through host memory in the e2e leg: keep the rank's threads (and, by first
+        # touch, its pinned buffers) on the CPU cores next to its GPU, or the ranks behind the other socket share one link
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local_rank))
+            numa_note = f"threads bound to the GPU-local cores (NVML): {len(os.sched_getaffinity(0))} of {os.cpu_count()}"
+        except Exception as e:  # noqa: BLE001 -- measurement hygiene only
+            numa_note = f"no CPU binding ({type(e).__name__})"
     stdout_fd = None
     if distributed:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
@@ -562,7 +574,8 @@ def run_ours(args):
         e2e_ms = float(tt.item())
         e2e = {"value": round(total / (e2e_ms * 1e-3) / 1e9, 3), "unit": UNIT, "h2d_bytes_per_step": 4 * n_local,
                "d2h_bytes_per_step": 4 * int(out.numel()), "ms_per_step": round(e2e_ms, 3),
-               "api": "multi.distributed_sort with pinned host buffers per rank", "timer": "CUDA events, max over ranks"}
+               "api": "multi.distributed_sort with pinned host buffers per rank", "timer": "CUDA events, max over ranks",
+               "host_placement": numa_note}
 
     cpu_baseline = None
     parity = {"sorted": True, "same_key_multiset_as_input": same_multiset}
