@@ -51,3 +51,13 @@ def test_harness_prefix_sum_histogram_and_pairs():
     assert out.count("-- Test Build Histogram --") == 4 and out.count("Bit Group: ") == 4
     out = _run("pairs", "--elems", "300001", "--blocks", "0,256", "--rs", "4,8")
     assert out.count("(key-value)") == 4
+
+
+@pytest.mark.gpu
+def test_harness_wide_digits_and_64bit_keys():
+    """r = 16 (the reference CPU path's other digit width, .cu:56-69) and 11 through the same driver, and the 64-bit mode;
+    every block self-checks against std::sort (a failed check makes _run fail)."""
+    out = _run("sort", "--elems", "1Mi,100003", "--blocks", "0", "--rs", "11,16")
+    assert out.count("-- Test GPU LSD Radix Sort --") == 4 and "R: 16" in out and "R: 11" in out
+    out = _run("sort64", "--elems", "1Mi,100003,7")
+    assert out.count("(64-bit keys)") == 3

@@ -6,6 +6,7 @@
 //     lsd_bench prefix_sum      [--elems ..] [--blocks ..]                                      (BenchmarkGPUPrefixSum,   :1083)
 //     lsd_bench build_histogram [--elems ..] [--blocks ..] [--rs ..]                            (BenchmarkBuildHistogram, :1124)
 //     lsd_bench pairs           [--elems ..] [--rs ..]                                          (key-value sort; no reference twin)
+//     lsd_bench sort64          [--elems ..]                                                    (64-bit keys; no reference twin)
 //
 // Defaults are the reference's sweep axes (elems 32 Mi, blocks 32..1024, rs 1,2,4,8; :1029-1062).  Differences, all on
 // purpose: the "CPU" line times this harness's own host checker (std::sort, a running sum, a counting loop -- what the
@@ -186,6 +187,38 @@ bool test_sort(size_t count, int block, int r, const Args& a, bool pairs)
     return report_check(ok);
 }
 
+// ---- 64-bit keys (lsd_sort64; no reference twin: the reference sorts uint32 only, .cu:62, :839) ---------------------
+bool test_sort64(size_t count, const Args& a)
+{
+    std::cout << "-- Test GPU LSD Radix Sort (64-bit keys) --" << std::endl;
+    const size_t size = count * sizeof(uint64_t);
+    const size_t ws_bytes = lsd_sort64_workspace_bytes(count);
+    std::cout << "Elements: " << gib((double)size) << " GB" << std::endl;
+    std::cout << "Histograms: " << gib((double)ws_bytes) << " GB" << std::endl;
+    std::cout << "Block Sums: " << 0 << " GB" << std::endl;
+    std::cout << "Block Size: " << 0 << std::endl;
+    std::cout << "R: " << 8 << std::endl;
+    std::mt19937_64 eng(a.seed);
+    std::vector<uint64_t> h_in(count), got(count);
+    for (auto& k : h_in) k = eng();
+    std::vector<uint64_t> want = h_in;
+    auto t0 = Clock::now();
+    std::sort(want.begin(), want.end());
+    const double cpu_ms = ms_since(t0);
+    std::cout << "CPU " << cpu_ms << " ms" << std::endl;
+    DeviceBuf d_a(size), d_b(size), d_src(size), d_ws(ws_bytes);
+    cudaStream_t s;
+    CK(cudaStreamCreate(&s));
+    CK(cudaMemcpy(d_src.p, h_in.data(), size, cudaMemcpyHostToDevice));
+    const float gpu_ms = timed(s, a.reps, [&] { CK(cudaMemcpyAsync(d_a.p, d_src.p, size, cudaMemcpyDeviceToDevice, s)); },
+                               [&] { LSD(lsd_sort64(d_a.as<uint64_t>(), d_b.as<uint64_t>(), count, LSD_KEY_U64, d_ws.p, ws_bytes, (lsd_stream_t)s)); });
+    CK(cudaMemcpy(got.data(), d_a.p, size, cudaMemcpyDeviceToHost));
+    std::cout << "GPU " << gpu_ms << " ms" << std::endl;
+    std::cout << "Speedup: x" << cpu_ms / gpu_ms << std::endl;
+    cudaStreamDestroy(s);
+    return report_check(got == want);
+}
+
 // ---- TestGPUPrefixSum (.cu:304-371) -------------------------------------------------------------------------------
 bool test_prefix_sum(size_t count, int block, const Args& a)
 {
@@ -247,7 +280,7 @@ bool test_build_histogram(size_t count, int block, int r, int bit_group, const A
 
 void usage()
 {
-    std::cerr << "usage: lsd_bench {sort|pairs|prefix_sum|build_histogram} [--elems N,..] [--blocks B,..] [--rs R,..] "
+    std::cerr << "usage: lsd_bench {sort|pairs|sort64|prefix_sum|build_histogram} [--elems N,..] [--blocks B,..] [--rs R,..] "
                  "[--seed S] [--reps K]\n";
 }
 
@@ -275,6 +308,8 @@ int main(int argc, char** argv)
         for (long long n : a.elems)
             for (long long b : a.blocks)
                 for (long long r : a.rs) ok = test_sort((size_t)n, (int)b, (int)r, a, mode == "pairs") && ok;
+    } else if (mode == "sort64") {
+        for (long long n : a.elems) ok = test_sort64((size_t)n, a) && ok;
     } else if (mode == "prefix_sum") {
         for (long long n : a.elems)
             for (long long b : a.blocks) ok = test_prefix_sum((size_t)n, (int)b, a) && ok;
