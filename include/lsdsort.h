@@ -220,12 +220,12 @@ typedef struct lsd_multi_stats {
     uint64_t n_in, n_out;   /* keys this rank brought / owns after the exchange */
     uint64_t n_out_max;     /* the largest share of any rank */
     uint64_t sent_bytes;    /* bytes that left this GPU over NVLink (excludes what it kept) */
-    uint32_t first_bucket;  /* top-digit buckets this rank owns: [first, last]; first > last when it owns none */
+    uint32_t first_bucket;  /* buckets of the exchange digit this rank owns: [first, last]; first > last when it owns none */
     uint32_t last_bucket;
     float plan_ms;          /* with lsd_multi_set_timing(ctx, 1): device time of histogram + all-gather + plan, */
     float exchange_ms;      /* of barrier + partition/exchange pass + barrier, */
     float sort_ms;          /* and of the local sort; 0 otherwise */
-    uint32_t reserved;
+    uint32_t exchange_digit; /* the digit the exchange partitioned on (3 = top); 0xFFFFFFFF: all keys equal, nothing moved */
 } lsd_multi_stats;
 
 typedef struct lsd_multi_ctx lsd_multi_ctx;

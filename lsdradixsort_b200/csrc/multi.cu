@@ -1,12 +1,14 @@
 // multi.cu -- lsd_sort_multi: the multi-GPU sort behind the C ABI (one process or thread per GPU, one node).
 //
 // No reference counterpart: the reference is single-GPU.  This is BASELINE.json's partitioning
-// (SURVEY 8(e)): top-digit histogram per rank -> the rows are all-gathered (their sum is the all-reduced MSD histogram)
+// (SURVEY 8(e)): digit histograms per rank -> the rows are all-gathered (their sum is the all-reduced MSD histogram)
 // -> every rank derives the same contiguous bucket -> rank map -> one pass kernel partitions the local keys by
 // destination and stores them straight into the owners' receive buffers over NVLink peer memory (CUDA IPC) -> local
-// LSD sort of what arrived.  Everything between the histogram and the exchange is planned ON THE DEVICE
-// (multi_plan_kernel): no host round trip sits in front of the exchange.  The host only learns how many keys it owns
-// (needed to enqueue the local sort) from a 64-byte copy on a side stream that overlaps the exchange pass.
+// LSD sort of what arrived.  The map is planned ON THE DEVICE (multi_plan_kernel); the host waits for 64 bytes of its
+// result (which digit to partition on, this rank's share) and enqueues the exchange pass and the local sort.
+// Skew: the exchange partitions on the HIGHEST DIGIT THAT VARIES over the whole input (all digits above it are constant,
+// so contiguous bucket ranges of that digit are contiguous key ranges): keys below 2^24, 2^16 or 2^8 are balanced over
+// their own top byte instead of landing on rank 0, and an input whose keys are all equal stays where it is.
 //
 // The two collectives (a 2 KiB all-gather and a barrier) come from the caller as callbacks, so liblsdsort has no link
 // dependency on a communication library; include/lsdsort_nccl.h supplies them for an ncclComm_t, lsdradixsort_b200/
@@ -21,7 +23,8 @@
 
 namespace lsd {
 
-constexpr int kMultiBuckets = 256;  // the exchange partitions on the top 8-bit digit
+constexpr int kMultiBuckets = 256;  // the exchange partitions on one 8-bit digit
+constexpr int kMultiDigits = 4;
 constexpr int kMultiMaxRanks = 64;
 
 struct MultiResult {              // written by multi_plan_kernel, copied to the host
@@ -31,13 +34,16 @@ struct MultiResult {              // written by multi_plan_kernel, copied to the
     uint32_t overflow;            // some rank's share exceeds the capacity: nothing is moved
     uint32_t first_bucket;        // this rank's bucket range [first, last]; first > last when it owns nothing
     uint32_t last_bucket;
-    uint32_t pad[7];
+    uint32_t digit;               // the digit the exchange partitions on: the highest one that varies over the input
+    uint32_t keep_local;          // every key of every rank is the same: nothing to exchange, each rank keeps its keys
+    uint32_t pad[5];
 };
 static_assert(sizeof(MultiResult) == 64, "copied as 64 bytes");
 
-// One CTA of 256 threads (one per bucket).  per_rank: [nranks][256] top-digit counts (the all-gathered rows).
-// bucket b goes to rank floor(nranks * (keys before b + half of b) / total), made monotone: every rank owns a contiguous
-// run of buckets whose total is as close to total / nranks as whole buckets allow (the same rule as multi.assign_buckets).
+// One CTA of 256 threads (one per bucket).  per_rank: [nranks][4][256] digit counts (the all-gathered histograms).
+// The exchange digit is the highest digit whose global histogram is not a single bucket.  Bucket b of that digit goes to
+// rank floor(nranks * (keys before b + half of b) / total), made monotone: every rank owns a contiguous run of buckets
+// whose total is as close to total / nranks as whole buckets allow (the same rule as multi.assign_buckets).
 __global__ void __launch_bounds__(kMultiBuckets)
 multi_plan_kernel(const uint64_t* __restrict__ per_rank, int nranks, int rank, const uint64_t* __restrict__ peer_ptrs,
                   uint64_t capacity, uint64_t* __restrict__ dst_ptrs, uint32_t* __restrict__ dst_seg,
@@ -51,8 +57,56 @@ multi_plan_kernel(const uint64_t* __restrict__ per_rank, int nranks, int rank, c
     __shared__ uint64_t s_mine[kMultiMaxRanks];    // keys I send to d
     __shared__ uint32_t s_first[kMultiMaxRanks], s_last[kMultiMaxRanks];
     const int b = threadIdx.x;
+    constexpr size_t kRow = (size_t)kMultiDigits * kMultiBuckets;  // one rank's histograms
+    // total number of keys (any digit's histogram sums to it)
     uint64_t tot = 0;
-    for (int s = 0; s < nranks; ++s) tot += per_rank[(size_t)s * kMultiBuckets + b];
+    for (int s = 0; s < nranks; ++s) tot += per_rank[s * kRow + (size_t)(kMultiDigits - 1) * kMultiBuckets + b];
+    s_scan[b] = tot;
+    __syncthreads();
+    for (int o = kMultiBuckets / 2; o > 0; o >>= 1) {
+        if (b < o) s_scan[b] += s_scan[b + o];
+        __syncthreads();
+    }
+    const uint64_t grand = s_scan[0];
+    __syncthreads();
+    // the highest digit that varies
+    int digit = kMultiDigits - 1;
+    int constant = 1;
+    for (int p = kMultiDigits - 1; p >= 0; --p) {
+        uint64_t t = 0;
+        for (int s = 0; s < nranks; ++s) t += per_rank[s * kRow + (size_t)p * kMultiBuckets + b];
+        constant = __syncthreads_or(t == grand);  // one bucket holds every key (also true for an empty input)
+        if (!constant) {
+            digit = p;
+            tot = t;
+            break;
+        }
+    }
+    const uint64_t* rows = per_rank + (size_t)digit * kMultiBuckets;  // row of rank s: rows[s * kRow + b]
+    if (constant) {
+        // all keys are equal (or there are none): every rank keeps what it has
+        dst_ptrs[b] = peer_ptrs[rank];
+        dst_seg[b] = 0u | ((uint32_t)(kMultiBuckets - 1) << 16);
+        if (b == 0) {
+            uint64_t mine = 0, mx = 0;
+            for (int s = 0; s < nranks; ++s) {
+                uint64_t ns = 0;
+                for (int q = 0; q < kMultiBuckets; ++q) ns += per_rank[s * kRow + q];
+                mx = ns > mx ? ns : mx;
+                if (s == rank) mine = ns;
+            }
+            result->n_out = mine;
+            result->n_out_max = mx;
+            result->sent = 0;
+            result->overflow = mx > capacity ? 1u : 0u;
+            result->first_bucket = 0;
+            result->last_bucket = kMultiBuckets - 1;
+            result->digit = 0;
+            result->keep_local = 1;
+            *abort_flag = 1u;
+        }
+        return;
+    }
     s_tot[b] = tot;
     s_scan[b] = tot;
     if (b < kMultiMaxRanks) {
@@ -69,11 +123,8 @@ multi_plan_kernel(const uint64_t* __restrict__ per_rank, int nranks, int rank, c
         s_scan[b] += t;
         __syncthreads();
     }
-    const uint64_t grand = s_scan[kMultiBuckets - 1];
     int owner;
-    if (grand == 0) {
-        owner = b * nranks / kMultiBuckets;
-    } else {
+    {
         const uint64_t twice_mid = 2 * (s_scan[b] - tot) + tot;  // < 2^41: the product below fits 64 bits for nranks <= 64
         const uint64_t o = twice_mid * (uint64_t)nranks / (2 * grand);
         owner = (int)(o < (uint64_t)(nranks - 1) ? o : (uint64_t)(nranks - 1));
@@ -91,9 +142,9 @@ multi_plan_kernel(const uint64_t* __restrict__ per_rank, int nranks, int rank, c
     // per destination: total share, what the sources ahead of me send, what I send, its bucket range
     atomicAdd(reinterpret_cast<unsigned long long*>(&s_share[owner]), (unsigned long long)tot);
     uint64_t ahead = 0;
-    for (int s = 0; s < rank; ++s) ahead += per_rank[(size_t)s * kMultiBuckets + b];
+    for (int s = 0; s < rank; ++s) ahead += rows[s * kRow + b];
     atomicAdd(reinterpret_cast<unsigned long long*>(&s_before[owner]), (unsigned long long)ahead);
-    atomicAdd(reinterpret_cast<unsigned long long*>(&s_mine[owner]), (unsigned long long)per_rank[(size_t)rank * kMultiBuckets + b]);
+    atomicAdd(reinterpret_cast<unsigned long long*>(&s_mine[owner]), (unsigned long long)rows[(size_t)rank * kRow + b]);
     atomicMin(&s_first[owner], (uint32_t)b);
     atomicMax(&s_last[owner], (uint32_t)b);
     __syncthreads();
@@ -113,6 +164,8 @@ multi_plan_kernel(const uint64_t* __restrict__ per_rank, int nranks, int rank, c
         result->overflow = mx > capacity ? 1u : 0u;
         result->first_bucket = s_first[rank];
         result->last_bucket = s_last[rank];
+        result->digit = (uint32_t)digit;
+        result->keep_local = 0;
         *abort_flag = mx > capacity ? 1u : 0u;
     }
 }
@@ -175,7 +228,7 @@ LSD_API int lsd_multi_ctx_create(const lsd_multi_comm* comm, uint32_t* recv, uin
     if (c->sort_ws_bytes == 0) return fail(LSD_ERR_UNSUPPORTED);
     size_t off = 0;
     c->off_hist = off;    off = align256(off + sizeof(uint64_t) * (32 / r) * kMultiBuckets);
-    c->off_gather = off;  off = align256(off + sizeof(uint64_t) * (size_t)N * kMultiBuckets);
+    c->off_gather = off;  off = align256(off + sizeof(uint64_t) * (size_t)N * kMultiDigits * kMultiBuckets);
     c->off_peers = off;   off = align256(off + sizeof(uint64_t) * N);
     c->off_dst = off;     off = align256(off + sizeof(uint64_t) * kMultiBuckets);
     c->off_seg = off;     off = align256(off + sizeof(uint32_t) * kMultiBuckets);
@@ -190,7 +243,7 @@ LSD_API int lsd_multi_ctx_create(const lsd_multi_comm* comm, uint32_t* recv, uin
     if (cudaEventCreateWithFlags(&c->ev_copied, cudaEventDisableTiming) != cudaSuccess) return fail(LSD_ERR_CUDA);
 
     // exchange the receive buffers' addresses through the all-gather callback (96 bytes per rank, staged in the gather
-    // area, which holds 2 KiB per rank): a CUDA IPC handle for ranks in other processes, the plain pointer (plus peer
+    // area, which holds 8 KiB per rank): a CUDA IPC handle for ranks in other processes, the plain pointer (plus peer
     // access) for ranks that are threads of this process
     struct Handle { unsigned char h[64]; uint64_t off; uint64_t raw; int64_t pid; int32_t device; int32_t pad; };
     static_assert(sizeof(Handle) == 96, "96 bytes per rank");
@@ -275,33 +328,22 @@ LSD_API int lsd_sort_multi(lsd_multi_ctx* c, const uint32_t* keys, uint64_t n_lo
     uint32_t* abort_flag = reinterpret_cast<uint32_t*>(c->ws + c->off_abort);
     MultiResult* result = reinterpret_cast<MultiResult*>(c->ws + c->off_result);
     void* sort_ws = c->ws + c->off_sort;
-    const int top = 32 / c->r - 1;
 
     c->timed = false;
     if (c->timing) LSD_CUDA_TRY(cudaEventRecord(c->ev_t[0], s));
-    // 1. top-digit histogram of the local keys: row `top` of the [32/r][256] layout
-    int rc = lsd_top_digit_histogram(keys, n_local, c->r, hist, stream);
+    // 1. digit histograms of the local keys ([4][256]: one read; the exchange digit is chosen from all four)
+    int rc = launch_digit_histograms(keys, n_local, c->r, hist, s);
     if (rc != LSD_OK) return rc;
-    // 2. the rows of all ranks (their sum is the all-reduced MSD histogram)
-    if (comm.all_gather(comm.ctx, hist + (size_t)top * kMultiBuckets, gathered, sizeof(uint64_t) * kMultiBuckets, stream) != 0)
-        return LSD_ERR_COMM;
-    // 3. bucket -> rank map, destination pointers and segments, shares: on the device
+    // 2. the histograms of all ranks (their sum is the all-reduced histogram of every digit)
+    if (comm.all_gather(comm.ctx, hist, gathered, sizeof(uint64_t) * kMultiDigits * kMultiBuckets, stream) != 0) return LSD_ERR_COMM;
+    // 3. exchange digit, bucket -> rank map, destination pointers and segments, shares: on the device
     multi_plan_kernel<<<1, kMultiBuckets, 0, s>>>(gathered, N, comm.rank, peers, c->capacity, dst, seg, abort_flag, result);
     LSD_LAUNCH_CHECK();
-    LSD_CUDA_TRY(cudaEventRecord(c->ev_plan, s));
-    LSD_CUDA_TRY(cudaStreamWaitEvent(c->side, c->ev_plan, 0));
-    LSD_CUDA_TRY(cudaMemcpyAsync(c->host_result, result, sizeof(MultiResult), cudaMemcpyDeviceToHost, c->side));
-    LSD_CUDA_TRY(cudaEventRecord(c->ev_copied, c->side));
+    // the host needs 64 bytes of the plan: which digit the exchange pass partitions on (its kernel is instantiated per
+    // digit position) and this rank's share (to enqueue the local sort)
+    LSD_CUDA_TRY(cudaMemcpyAsync(c->host_result, result, sizeof(MultiResult), cudaMemcpyDeviceToHost, s));
+    LSD_CUDA_TRY(cudaEventRecord(c->ev_copied, s));
     if (c->timing) LSD_CUDA_TRY(cudaEventRecord(c->ev_t[1], s));
-    // 4. fused partition + exchange: every rank is done reading what the previous exchange left in its buffer, then the
-    //    pass stores each destination segment into its owner's buffer, then every rank's stores have landed.  The pass
-    //    is skipped on the device (abort_flag) when some rank's share exceeds its buffer.
-    if (comm.barrier(comm.ctx, stream) != 0) return LSD_ERR_COMM;
-    rc = pass_enqueue(keys, nullptr, n_local, c->r, top, 0, sort_ws, c->sort_ws_bytes, nullptr, s, dst, seg, abort_flag);
-    if (rc != LSD_OK) return rc;
-    if (comm.barrier(comm.ctx, stream) != 0) return LSD_ERR_COMM;
-    if (c->timing) LSD_CUDA_TRY(cudaEventRecord(c->ev_t[2], s));
-    // the host needs its share to enqueue the local sort: the 64-byte copy ran beside the exchange pass
     LSD_CUDA_TRY(cudaEventSynchronize(c->ev_copied));
     const MultiResult res = *c->host_result;
     c->last.n_in = n_local;
@@ -310,11 +352,23 @@ LSD_API int lsd_sort_multi(lsd_multi_ctx* c, const uint32_t* keys, uint64_t n_lo
     c->last.sent_bytes = 4 * res.sent;
     c->last.first_bucket = res.first_bucket;
     c->last.last_bucket = res.last_bucket;
+    c->last.exchange_digit = res.keep_local ? 0xFFFFFFFFu : res.digit;
     *n_out = res.n_out;
-    if (res.overflow) {  // identical on every rank: all return the same status, nothing was moved
+    if (res.overflow) {  // identical on every rank: all return the same status, nothing is moved
         *n_out = res.n_out_max;
         return LSD_ERR_CAPACITY;
     }
+    // 4. fused partition + exchange on the chosen digit: every rank is done reading what the previous exchange left in its
+    //    buffer, then the pass stores each destination segment into its owner's buffer, then every rank's stores have landed
+    if (comm.barrier(comm.ctx, stream) != 0) return LSD_ERR_COMM;
+    if (res.keep_local) {  // all keys equal: nothing to exchange, the rank's keys are its slice
+        if (n_local > 0) LSD_CUDA_TRY(cudaMemcpyAsync(c->recv, keys, sizeof(uint32_t) * n_local, cudaMemcpyDeviceToDevice, s));
+    } else {
+        rc = pass_enqueue(keys, nullptr, n_local, c->r, (int)res.digit, 0, sort_ws, c->sort_ws_bytes, nullptr, s, dst, seg, abort_flag);
+        if (rc != LSD_OK) return rc;
+    }
+    if (comm.barrier(comm.ctx, stream) != 0) return LSD_ERR_COMM;
+    if (c->timing) LSD_CUDA_TRY(cudaEventRecord(c->ev_t[2], s));
     // 5. local LSD sort of the owned key range
     rc = lsd_sort(c->recv, scratch, res.n_out, c->r, 0, sort_ws, c->sort_ws_bytes, stream);
     if (rc != LSD_OK) return rc;

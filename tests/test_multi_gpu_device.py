@@ -89,7 +89,7 @@ def _run(world, kind, n_local):
     assert all(r[6] for r in results), "an aborted exchange must not move any key"
 
 
-@pytest.mark.parametrize("kind", ["uniform", "entropy4_table", "sorted"])
+@pytest.mark.parametrize("kind", ["uniform", "entropy4_table", "sorted", "low_nibble", "all_equal"])
 def test_distributed_sort_two_gpus_peer_and_nccl(kind):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs on the box")

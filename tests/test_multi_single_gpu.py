@@ -76,7 +76,8 @@ def _rank_main(rank, comm, keys_np, capacity, results, errors):
         lib.lsd_multi_last_stats(ctx, C.byref(ms))
         comm.bar.wait()  # nobody unmaps while a peer may still be writing
         results[rank] = (st, int(n_out.value), recv[: int(n_out.value)].cpu().numpy().view(np.uint32).copy() if st == 0 else None,
-                         bool((recv == 0x5A5A5A5A).all()) if st != 0 else None, (int(ms.first_bucket), int(ms.last_bucket), int(ms.n_out_max)))
+                         bool((recv == 0x5A5A5A5A).all()) if st != 0 else None,
+                         (int(ms.first_bucket), int(ms.last_bucket), int(ms.n_out_max), int(ms.exchange_digit)))
         lib.lsd_multi_ctx_destroy(ctx)
     except Exception as e:  # noqa: BLE001
         errors.append((rank, repr(e)))
@@ -86,9 +87,18 @@ def _rank_main(rank, comm, keys_np, capacity, results, errors):
             pass
 
 
+def _keys(kind, n, seed):
+    if kind == "small_range":     # keys below 2^12: digits 3 and 2 are constant, the exchange partitions on digit 1
+        return (keygen.make_keys("uniform", n, seed) & np.uint32(0xFFF)).astype(np.uint32)
+    if kind == "heavy_bucket":    # 90 % of the keys share one top-digit bucket: a rank's share exceeds any sane slack
+        u = keygen.make_keys("uniform", n, seed)
+        return np.where(u % np.uint32(10) != 0, u & np.uint32(0x00FFFFFF), u).astype(np.uint32)
+    return keygen.make_keys(kind, n, seed)
+
+
 def _run(world, kind, n_local, capacity):
     comm = ThreadComm(world)
-    keys = [keygen.make_keys(kind, n_local, seed=900 + r) for r in range(world)]
+    keys = [_keys(kind, n_local, seed=900 + r) for r in range(world)]
     results, errors = [None] * world, []
     threads = [threading.Thread(target=_rank_main, args=(r, comm, keys[r], capacity, results, errors)) for r in range(world)]
     for t in threads:
@@ -100,7 +110,7 @@ def _run(world, kind, n_local, capacity):
 
 
 @pytest.mark.parametrize("world", [1, 2, 3, 4])
-@pytest.mark.parametrize("kind", ["uniform", "entropy4_table", "sorted", "all_equal"])
+@pytest.mark.parametrize("kind", ["uniform", "entropy4_table", "sorted"])
 def test_sort_multi_threads_on_one_gpu(world, kind):
     n_local = 200_000 + 17 * world
     keys, results = _run(world, kind, n_local, capacity=n_local * world + 64)
@@ -108,10 +118,14 @@ def test_sort_multi_threads_on_one_gpu(world, kind):
     whole = np.sort(np.concatenate(keys))
     assert np.array_equal(np.concatenate([r[2] for r in results]), whole)  # rank order == global order
     assert sum(r[1] for r in results) == whole.size
-    # the device-side plan is the same map the host-side numpy plan derives (multi.assign_buckets)
-    per_rank = np.stack([np.bincount(k >> np.uint32(24), minlength=256) for k in keys]).astype(np.int64)
+    # the device-side plan is the map the host-side numpy plan derives (multi.assign_buckets) from the histogram of the
+    # highest digit that varies (the top one unless the keys are small: "sorted" at this size stays below 2^24)
+    allk = np.concatenate(keys)
+    digit = max(p for p in range(4) if np.unique((allk >> np.uint32(8 * p)) & np.uint32(255)).size > 1)
+    per_rank = np.stack([np.bincount((k >> np.uint32(8 * digit)) & np.uint32(255), minlength=256) for k in keys]).astype(np.int64)
     owner = multi.assign_buckets(per_rank.sum(axis=0), world)
     for r, res in enumerate(results):
+        assert res[4][3] == digit
         mine = np.nonzero(owner == r)[0]
         if mine.size:
             assert res[4][0] == int(mine[0]) and res[4][1] == int(mine[-1])
@@ -120,12 +134,39 @@ def test_sort_multi_threads_on_one_gpu(world, kind):
         assert res[1] == int(per_rank[:, owner == r].sum())
 
 
+@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("kind,digit", [("low_nibble", 0), ("small_range", 1)])
+def test_sort_multi_partitions_on_the_highest_varying_digit(world, kind, digit):
+    """BASELINE config 4 x config 5: keys whose top digits are constant are balanced over the highest digit that varies
+    instead of landing on one rank -- the ordinary 25 % slack is enough."""
+    n_local = 150_000 + world
+    keys, results = _run(world, kind, n_local, capacity=int(n_local * 1.25) + 64)
+    assert all(r[0] == N.LSD_OK for r in results), [r[0] for r in results]
+    assert all(r[4][3] == digit for r in results)
+    whole = np.sort(np.concatenate(keys))
+    assert np.array_equal(np.concatenate([r[2] for r in results]), whole)
+    shares = [r[1] for r in results]
+    assert max(shares) <= 1.25 * n_local and min(shares) >= 0.5 * n_local, shares
+
+
+@pytest.mark.parametrize("world", [1, 3])
+def test_sort_multi_all_equal_keys_stay_where_they_are(world):
+    n_local = 100_000 + 3 * world
+    keys, results = _run(world, "all_equal", n_local, capacity=n_local + 64)
+    assert all(r[0] == N.LSD_OK for r in results)
+    assert all(r[4][3] == 0xFFFFFFFF and r[1] == n_local for r in results)  # nothing moved
+    assert np.array_equal(np.concatenate([r[2] for r in results]), np.sort(np.concatenate(keys)))
+
+
 def test_sort_multi_capacity_status_on_every_rank_and_nothing_moves():
     world, n_local = 3, 100_000
-    keys, results = _run(world, "all_equal", n_local, capacity=n_local + 64)  # one bucket: everything lands on one rank
+    keys, results = _run(world, "heavy_bucket", n_local, capacity=int(n_local * 1.25))  # one bucket holds 90 % of the keys
     assert [r[0] for r in results] == [N.LSD_ERR_CAPACITY] * world
-    assert all(r[1] == n_local * world for r in results)  # *n_out reports the largest share
+    assert len({r[1] for r in results}) == 1 and results[0][1] > 2 * n_local  # *n_out reports the largest share, everywhere
     assert all(r[3] for r in results)  # receive buffers untouched
+    keys, results = _run(world, "heavy_bucket", n_local, capacity=results[0][1] + 64)  # the retry the status asks for
+    assert all(r[0] == N.LSD_OK for r in results)
+    assert np.array_equal(np.concatenate([r[2] for r in results]), np.sort(np.concatenate(keys)))
 
 
 def test_sort_multi_larger_uniform_two_ranks():
