@@ -196,11 +196,14 @@ LSD_API int lsd_ipc_close(void *peer_ptr, uint64_t offset);
 
 /* ---------------------------------------------------------------------------------------
  * Multi-GPU sort (one process or thread per GPU, one node).  No reference counterpart: the reference is single-GPU
- * (SURVEY 2.4); this is BASELINE.json's partitioning: every rank histograms the top 8-bit digit of its
- * keys, the 256-bin rows are all-gathered (their sum is the all-reduced MSD histogram), every rank derives the same
- * contiguous bucket -> rank map ON THE DEVICE, one pass kernel partitions the local keys by owner and stores them
- * straight into the owners' receive buffers over NVLink peer memory (CUDA IPC; lsd_sort_pass_scatter), and every rank
- * sorts what arrived.  Rank k ends with the k-th slice of the global order in its receive buffer.
+ * (SURVEY 2.4); this is BASELINE.json's partitioning: every rank histograms the 8-bit digits of its keys
+ * (one read), the [4][256] histograms are all-gathered (their sum is the all-reduced histogram of every digit), every
+ * rank derives the same contiguous bucket -> rank map ON THE DEVICE for the highest digit that VARIES over the whole
+ * input -- the top one unless the keys are small (below 2^24, 2^16, 2^8: all digits above it are constant, so bucket
+ * ranges of that digit are still contiguous key ranges and such inputs are balanced instead of landing on rank 0); one pass
+ * kernel partitions the local keys by owner on that digit and stores them straight into the owners' receive buffers over
+ * NVLink peer memory (CUDA IPC; lsd_sort_pass_scatter), and every rank sorts what arrived.  Rank k ends with the k-th
+ * slice of the global order in its receive buffer.  If every key of every rank is the same, nothing is exchanged.
  *
  * The two collectives are callbacks, so liblsdsort links no communication library: include/lsdsort_nccl.h fills an
  * lsd_multi_comm from an ncclComm_t, lsdradixsort_b200/multi.py from torch.distributed.  Both must be ordered on the
@@ -239,10 +242,11 @@ LSD_API int lsd_multi_ctx_destroy(lsd_multi_ctx *ctx);
 /* COLLECTIVE: sorts the union of every rank's `keys` (n_local <= max_n_local keys each, not modified).  On return the rank's slice
  * (*n_out keys, ascending; every key of rank k <= every key of rank k+1) is being written to the context's receive
  * buffer on `stream`; `scratch` (capacity keys) is ping-pong space for the local sort.  No host synchronisation sits
- * in front of the exchange; the call waits only for a 64-byte copy of the plan's result that overlaps the exchange pass
- * (the host needs *n_out to enqueue the local sort).  If any rank's share exceeds its capacity (a skewed top digit: the
- * balance is only as fine as one of the 256 buckets), EVERY rank returns LSD_ERR_CAPACITY, *n_out = the largest share
- * (so the caller can retry with bigger buffers) and no key is moved. */
+ * in front of the exchange other than the wait for a 64-byte copy of the plan's result (the digit to partition on and
+ * *n_out, which the host needs to enqueue the exchange pass and the local sort).  If any rank's share exceeds its
+ * capacity (the balance is only as fine as one of the 256 buckets of the exchange digit: a few very frequent key
+ * prefixes), EVERY rank returns LSD_ERR_CAPACITY, *n_out = the largest share (so the caller can retry with bigger
+ * buffers) and no key is moved. */
 LSD_API int lsd_sort_multi(lsd_multi_ctx *ctx, const uint32_t *keys, uint64_t n_local, uint32_t *scratch, uint64_t *n_out,
                            lsd_stream_t stream);
 /* Stats of the most recent lsd_sort_multi on this context.  With timing enabled the call synchronises the stream of
