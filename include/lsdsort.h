@@ -198,10 +198,12 @@ LSD_API int lsd_ipc_close(void *peer_ptr, uint64_t offset);
  * Multi-GPU sort (one process or thread per GPU, one node).  No reference counterpart: the reference is single-GPU
  * (SURVEY 2.4); this is BASELINE.json's partitioning: every rank histograms the 8-bit digits of its keys
  * (one read), the [4][256] histograms are all-gathered (their sum is the all-reduced histogram of every digit), every
- * rank derives the same contiguous bucket -> rank map ON THE DEVICE for the highest digit that VARIES over the whole
- * input -- the top one unless the keys are small (below 2^24, 2^16, 2^8: all digits above it are constant, so bucket
- * ranges of that digit are still contiguous key ranges and such inputs are balanced instead of landing on rank 0); one pass
- * kernel partitions the local keys by owner on that digit and stores them straight into the owners' receive buffers over
+ * rank derives the same contiguous bucket -> rank map ON THE DEVICE for the 8-bit window that ends at the highest BIT that
+ * varies over the whole input -- the top digit unless the keys live in a narrow range (all bits above the window are
+ * constant, so bucket ranges of the window are still contiguous key ranges: keys below 2^24, in [0, 2^17) or in
+ * [2^31, 2^31 + 1000) are balanced over their own 8 most significant varying bits instead of landing on one rank; a
+ * window that straddles two digits costs one more read of the keys for its histogram); one pass
+ * kernel partitions the local keys by owner on that window and stores them straight into the owners' receive buffers over
  * NVLink peer memory (CUDA IPC; lsd_sort_pass_scatter), and every rank sorts what arrived.  Rank k ends with the k-th
  * slice of the global order in its receive buffer.  If every key of every rank is the same, nothing is exchanged.
  *
@@ -223,12 +225,13 @@ typedef struct lsd_multi_stats {
     uint64_t n_in, n_out;   /* keys this rank brought / owns after the exchange */
     uint64_t n_out_max;     /* the largest share of any rank */
     uint64_t sent_bytes;    /* bytes that left this GPU over NVLink (excludes what it kept) */
-    uint32_t first_bucket;  /* buckets of the exchange digit this rank owns: [first, last]; first > last when it owns none */
+    uint32_t first_bucket;  /* buckets of the exchange window this rank owns: [first, last]; first > last when it owns none */
     uint32_t last_bucket;
     float plan_ms;          /* with lsd_multi_set_timing(ctx, 1): device time of histogram + all-gather + plan, */
     float exchange_ms;      /* of barrier + partition/exchange pass + barrier, */
     float sort_ms;          /* and of the local sort; 0 otherwise */
-    uint32_t exchange_digit; /* the digit the exchange partitioned on (3 = top); 0xFFFFFFFF: all keys equal, nothing moved */
+    uint32_t exchange_shift; /* the exchange partitioned on bits [shift, shift + 8) (24 = the top digit); 0xFFFFFFFF: all keys
+                                equal, nothing moved */
 } lsd_multi_stats;
 
 typedef struct lsd_multi_ctx lsd_multi_ctx;

@@ -72,7 +72,7 @@ class MultiStats(C.Structure):
         ("plan_ms", C.c_float),
         ("exchange_ms", C.c_float),
         ("sort_ms", C.c_float),
-        ("exchange_digit", C.c_uint32),
+        ("exchange_shift", C.c_uint32),
     ]
 
 

@@ -6,9 +6,10 @@
 // destination and stores them straight into the owners' receive buffers over NVLink peer memory (CUDA IPC) -> local
 // LSD sort of what arrived.  The map is planned ON THE DEVICE (multi_plan_kernel); the host waits for 64 bytes of its
 // result (which digit to partition on, this rank's share) and enqueues the exchange pass and the local sort.
-// Skew: the exchange partitions on the HIGHEST DIGIT THAT VARIES over the whole input (all digits above it are constant,
-// so contiguous bucket ranges of that digit are contiguous key ranges): keys below 2^24, 2^16 or 2^8 are balanced over
-// their own top byte instead of landing on rank 0, and an input whose keys are all equal stays where it is.
+// Skew: the exchange partitions on the 8-bit WINDOW THAT ENDS AT THE HIGHEST BIT THAT VARIES over the whole input (all bits
+// above it are constant, so contiguous bucket ranges of the window are contiguous key ranges): keys in any range -- below
+// 2^24, in [0, 2^17), in [2^31, 2^31 + 1000) -- are balanced over their own 8 most significant varying bits instead of
+// landing on one rank, and an input whose keys are all equal stays where it is.
 //
 // The two collectives (a 2 KiB all-gather and a barrier) come from the caller as callbacks, so liblsdsort has no link
 // dependency on a communication library; include/lsdsort_nccl.h supplies them for an ncclComm_t, lsdradixsort_b200/
@@ -34,22 +35,23 @@ struct MultiResult {              // written by multi_plan_kernel, copied to the
     uint32_t overflow;            // some rank's share exceeds the capacity: nothing is moved
     uint32_t first_bucket;        // this rank's bucket range [first, last]; first > last when it owns nothing
     uint32_t last_bucket;
-    uint32_t digit;               // the digit the exchange partitions on: the highest one that varies over the input
+    uint32_t shift;               // the exchange partitions on bits [shift, shift + 8): the window that ends at the highest
+                                  // bit that varies over the input (24 = the top digit)
     uint32_t keep_local;          // every key of every rank is the same: nothing to exchange, each rank keeps its keys
-    uint32_t pad[5];
+    uint32_t need_window_hist;    // shift is not a multiple of 8: the map needs the histogram of that window first
+    uint32_t pad[4];
 };
 static_assert(sizeof(MultiResult) == 64, "copied as 64 bytes");
 
-// One CTA of 256 threads (one per bucket).  per_rank: [nranks][4][256] digit counts (the all-gathered histograms).
-// The exchange digit is the highest digit whose global histogram is not a single bucket.  Bucket b of that digit goes to
-// rank floor(nranks * (keys before b + half of b) / total), made monotone: every rank owns a contiguous run of buckets
-// whose total is as close to total / nranks as whole buckets allow (the same rule as multi.assign_buckets).
-__global__ void __launch_bounds__(kMultiBuckets)
-multi_plan_kernel(const uint64_t* __restrict__ per_rank, int nranks, int rank, const uint64_t* __restrict__ peer_ptrs,
-                  uint64_t capacity, uint64_t* __restrict__ dst_ptrs, uint32_t* __restrict__ dst_seg,
-                  uint32_t* __restrict__ abort_flag, MultiResult* __restrict__ result)
+// Bucket -> rank map for one 8-bit window.  rows: the window's histogram of rank s is rows[s * stride + b].
+// Bucket b goes to rank floor(nranks * (keys before b + half of b) / total), made monotone: every rank owns a contiguous
+// run of buckets whose total is as close to total / nranks as whole buckets allow (the same rule as multi.assign_buckets).
+// Called by all 256 threads of the plan CTA; tot = this thread's bucket total, grand = number of keys (> 0).
+__device__ void multi_plan_map(const uint64_t* __restrict__ rows, size_t stride, uint64_t tot, uint64_t grand, int nranks, int rank,
+                               const uint64_t* __restrict__ peer_ptrs, uint64_t capacity, uint64_t* __restrict__ dst_ptrs,
+                               uint32_t* __restrict__ dst_seg, uint32_t* __restrict__ abort_flag, MultiResult* __restrict__ result,
+                               uint32_t shift)
 {
-    __shared__ uint64_t s_tot[kMultiBuckets];
     __shared__ uint64_t s_scan[kMultiBuckets];
     __shared__ int s_owner[kMultiBuckets];
     __shared__ uint64_t s_share[kMultiMaxRanks];   // keys owned by rank d
@@ -57,57 +59,6 @@ multi_plan_kernel(const uint64_t* __restrict__ per_rank, int nranks, int rank, c
     __shared__ uint64_t s_mine[kMultiMaxRanks];    // keys I send to d
     __shared__ uint32_t s_first[kMultiMaxRanks], s_last[kMultiMaxRanks];
     const int b = threadIdx.x;
-    constexpr size_t kRow = (size_t)kMultiDigits * kMultiBuckets;  // one rank's histograms
-    // total number of keys (any digit's histogram sums to it)
-    uint64_t tot = 0;
-    for (int s = 0; s < nranks; ++s) tot += per_rank[s * kRow + (size_t)(kMultiDigits - 1) * kMultiBuckets + b];
-    s_scan[b] = tot;
-    __syncthreads();
-    for (int o = kMultiBuckets / 2; o > 0; o >>= 1) {
-        if (b < o) s_scan[b] += s_scan[b + o];
-        __syncthreads();
-    }
-    const uint64_t grand = s_scan[0];
-    __syncthreads();
-    // the highest digit that varies
-    int digit = kMultiDigits - 1;
-    int constant = 1;
-    for (int p = kMultiDigits - 1; p >= 0; --p) {
-        uint64_t t = 0;
-        for (int s = 0; s < nranks; ++s) t += per_rank[s * kRow + (size_t)p * kMultiBuckets + b];
-        constant = __syncthreads_or(t == grand);  // one bucket holds every key (also true for an empty input)
-        if (!constant) {
-            digit = p;
-            tot = t;
-            break;
-        }
-    }
-    const uint64_t* rows = per_rank + (size_t)digit * kMultiBuckets;  // row of rank s: rows[s * kRow + b]
-    if (constant) {
-        // all keys are equal (or there are none): every rank keeps what it has
-        dst_ptrs[b] = peer_ptrs[rank];
-        dst_seg[b] = 0u | ((uint32_t)(kMultiBuckets - 1) << 16);
-        if (b == 0) {
-            uint64_t mine = 0, mx = 0;
-            for (int s = 0; s < nranks; ++s) {
-                uint64_t ns = 0;
-                for (int q = 0; q < kMultiBuckets; ++q) ns += per_rank[s * kRow + q];
-                mx = ns > mx ? ns : mx;
-                if (s == rank) mine = ns;
-            }
-            result->n_out = mine;
-            result->n_out_max = mx;
-            result->sent = 0;
-            result->overflow = mx > capacity ? 1u : 0u;
-            result->first_bucket = 0;
-            result->last_bucket = kMultiBuckets - 1;
-            result->digit = 0;
-            result->keep_local = 1;
-            *abort_flag = 1u;
-        }
-        return;
-    }
-    s_tot[b] = tot;
     s_scan[b] = tot;
     if (b < kMultiMaxRanks) {
         s_share[b] = 0;
@@ -142,9 +93,9 @@ multi_plan_kernel(const uint64_t* __restrict__ per_rank, int nranks, int rank, c
     // per destination: total share, what the sources ahead of me send, what I send, its bucket range
     atomicAdd(reinterpret_cast<unsigned long long*>(&s_share[owner]), (unsigned long long)tot);
     uint64_t ahead = 0;
-    for (int s = 0; s < rank; ++s) ahead += rows[s * kRow + b];
+    for (int s = 0; s < rank; ++s) ahead += rows[s * stride + b];
     atomicAdd(reinterpret_cast<unsigned long long*>(&s_before[owner]), (unsigned long long)ahead);
-    atomicAdd(reinterpret_cast<unsigned long long*>(&s_mine[owner]), (unsigned long long)rows[(size_t)rank * kRow + b]);
+    atomicAdd(reinterpret_cast<unsigned long long*>(&s_mine[owner]), (unsigned long long)rows[(size_t)rank * stride + b]);
     atomicMin(&s_first[owner], (uint32_t)b);
     atomicMax(&s_last[owner], (uint32_t)b);
     __syncthreads();
@@ -164,10 +115,120 @@ multi_plan_kernel(const uint64_t* __restrict__ per_rank, int nranks, int rank, c
         result->overflow = mx > capacity ? 1u : 0u;
         result->first_bucket = s_first[rank];
         result->last_bucket = s_last[rank];
-        result->digit = (uint32_t)digit;
+        result->shift = shift;
         result->keep_local = 0;
+        result->need_window_hist = 0;
         *abort_flag = mx > capacity ? 1u : 0u;
     }
+}
+
+// One CTA of 256 threads (one per bucket).  per_rank: [nranks][4][256] digit counts (the all-gathered histograms).
+// Finds the highest bit h that varies over the whole input (from the highest digit whose global histogram is not a single
+// bucket: the bits in which its live bucket numbers differ) and the exchange window [shift, shift + 8), shift = max(0, h - 7).
+// All bits above the window are constant, so contiguous bucket ranges of the window are contiguous key ranges, and the
+// window holds the 8 most significant varying bits: 256-way balance whatever the range of the keys.  A window that is a
+// digit (shift = 0, 8, 16, 24) is mapped at once; otherwise the caller histograms the window and runs multi_window_kernel.
+__global__ void __launch_bounds__(kMultiBuckets)
+multi_plan_kernel(const uint64_t* __restrict__ per_rank, int nranks, int rank, const uint64_t* __restrict__ peer_ptrs,
+                  uint64_t capacity, uint64_t* __restrict__ dst_ptrs, uint32_t* __restrict__ dst_seg,
+                  uint32_t* __restrict__ abort_flag, MultiResult* __restrict__ result)
+{
+    __shared__ uint64_t s_red[kMultiBuckets];
+    __shared__ uint32_t s_or, s_and;
+    const int b = threadIdx.x;
+    constexpr size_t kRow = (size_t)kMultiDigits * kMultiBuckets;  // one rank's histograms
+    // total number of keys (any digit's histogram sums to it)
+    uint64_t tot = 0;
+    for (int s = 0; s < nranks; ++s) tot += per_rank[s * kRow + (size_t)(kMultiDigits - 1) * kMultiBuckets + b];
+    s_red[b] = tot;
+    if (b == 0) { s_or = 0u; s_and = 0xFFu; }
+    __syncthreads();
+    for (int o = kMultiBuckets / 2; o > 0; o >>= 1) {
+        if (b < o) s_red[b] += s_red[b + o];
+        __syncthreads();
+    }
+    const uint64_t grand = s_red[0];
+    // the highest digit that varies
+    int digit = kMultiDigits - 1;
+    int constant = 1;
+    for (int p = kMultiDigits - 1; p >= 0; --p) {
+        uint64_t t = 0;
+        for (int s = 0; s < nranks; ++s) t += per_rank[s * kRow + (size_t)p * kMultiBuckets + b];
+        constant = __syncthreads_or(t == grand);  // one bucket holds every key (also true for an empty input)
+        if (!constant) {
+            digit = p;
+            tot = t;
+            break;
+        }
+    }
+    if (constant) {
+        // all keys are equal (or there are none): every rank keeps what it has
+        dst_ptrs[b] = peer_ptrs[rank];
+        dst_seg[b] = 0u | ((uint32_t)(kMultiBuckets - 1) << 16);
+        if (b == 0) {
+            uint64_t mine = 0, mx = 0;
+            for (int s = 0; s < nranks; ++s) {
+                uint64_t ns = 0;
+                for (int q = 0; q < kMultiBuckets; ++q) ns += per_rank[s * kRow + q];
+                mx = ns > mx ? ns : mx;
+                if (s == rank) mine = ns;
+            }
+            result->n_out = mine;
+            result->n_out_max = mx;
+            result->sent = 0;
+            result->overflow = mx > capacity ? 1u : 0u;
+            result->first_bucket = 0;
+            result->last_bucket = kMultiBuckets - 1;
+            result->shift = 0;
+            result->keep_local = 1;
+            result->need_window_hist = 0;
+            *abort_flag = 1u;
+        }
+        return;
+    }
+    // bits of this digit in which the live buckets differ
+    if (tot != 0) {
+        atomicOr(&s_or, (uint32_t)b);
+        atomicAnd(&s_and, (uint32_t)b);
+    }
+    __syncthreads();
+    const uint32_t varying = s_or & ~s_and;                       // != 0: at least two live buckets
+    const int h = 8 * digit + (31 - __clz((int)varying));         // highest varying bit of the keys
+    const uint32_t shift = h >= 7 ? (uint32_t)(h - 7) : 0u;
+    if ((shift & 7u) != 0u) {  // the window straddles two digits: its histogram is not among the four
+        if (b == 0) {
+            result->shift = shift;
+            result->keep_local = 0;
+            result->need_window_hist = 1;
+            result->overflow = 0;
+            result->n_out = result->n_out_max = result->sent = 0;
+        }
+        return;
+    }
+    const int wd = (int)(shift >> 3);  // == digit, or digit - 1 ... the aligned window that ends at or above h
+    uint64_t t = 0;
+    for (int s = 0; s < nranks; ++s) t += per_rank[s * kRow + (size_t)wd * kMultiBuckets + b];
+    multi_plan_map(per_rank + (size_t)wd * kMultiBuckets, kRow, t, grand, nranks, rank, peer_ptrs, capacity, dst_ptrs, dst_seg,
+                   abort_flag, result, shift);
+}
+
+// The map for a window whose histogram was taken separately: rows = [nranks][256] counts of ((key >> shift) & 255).
+__global__ void __launch_bounds__(kMultiBuckets)
+multi_window_kernel(const uint64_t* __restrict__ rows, int nranks, int rank, const uint64_t* __restrict__ peer_ptrs,
+                    uint64_t capacity, uint64_t* __restrict__ dst_ptrs, uint32_t* __restrict__ dst_seg,
+                    uint32_t* __restrict__ abort_flag, MultiResult* __restrict__ result, uint32_t shift)
+{
+    __shared__ uint64_t s_red[kMultiBuckets];
+    const int b = threadIdx.x;
+    uint64_t tot = 0;
+    for (int s = 0; s < nranks; ++s) tot += rows[(size_t)s * kMultiBuckets + b];
+    s_red[b] = tot;
+    __syncthreads();
+    for (int o = kMultiBuckets / 2; o > 0; o >>= 1) {
+        if (b < o) s_red[b] += s_red[b + o];
+        __syncthreads();
+    }
+    multi_plan_map(rows, kMultiBuckets, tot, s_red[0], nranks, rank, peer_ptrs, capacity, dst_ptrs, dst_seg, abort_flag, result, shift);
 }
 
 }  // namespace lsd
@@ -339,12 +400,25 @@ LSD_API int lsd_sort_multi(lsd_multi_ctx* c, const uint32_t* keys, uint64_t n_lo
     // 3. exchange digit, bucket -> rank map, destination pointers and segments, shares: on the device
     multi_plan_kernel<<<1, kMultiBuckets, 0, s>>>(gathered, N, comm.rank, peers, c->capacity, dst, seg, abort_flag, result);
     LSD_LAUNCH_CHECK();
-    // the host needs 64 bytes of the plan: which digit the exchange pass partitions on (its kernel is instantiated per
-    // digit position) and this rank's share (to enqueue the local sort)
+    // the host needs 64 bytes of the plan: where the exchange window sits (the pass kernel is instantiated per digit
+    // position, with a run-time form for the others) and this rank's share (to enqueue the local sort)
     LSD_CUDA_TRY(cudaMemcpyAsync(c->host_result, result, sizeof(MultiResult), cudaMemcpyDeviceToHost, s));
     LSD_CUDA_TRY(cudaEventRecord(c->ev_copied, s));
-    if (c->timing) LSD_CUDA_TRY(cudaEventRecord(c->ev_t[1], s));
     LSD_CUDA_TRY(cudaEventSynchronize(c->ev_copied));
+    if (c->host_result->need_window_hist) {
+        // the 8 most significant varying bits straddle two digits (keys in a range like [0, 2^17)): histogram that window
+        // (one more read of the local keys), gather the 2 KiB rows, map
+        const uint32_t shift = c->host_result->shift;
+        rc = launch_field_histogram(keys, n_local, (int)shift, 8, hist, s);
+        if (rc != LSD_OK) return rc;
+        if (comm.all_gather(comm.ctx, hist, gathered, sizeof(uint64_t) * kMultiBuckets, stream) != 0) return LSD_ERR_COMM;
+        multi_window_kernel<<<1, kMultiBuckets, 0, s>>>(gathered, N, comm.rank, peers, c->capacity, dst, seg, abort_flag, result, shift);
+        LSD_LAUNCH_CHECK();
+        LSD_CUDA_TRY(cudaMemcpyAsync(c->host_result, result, sizeof(MultiResult), cudaMemcpyDeviceToHost, s));
+        LSD_CUDA_TRY(cudaEventRecord(c->ev_copied, s));
+        LSD_CUDA_TRY(cudaEventSynchronize(c->ev_copied));
+    }
+    if (c->timing) LSD_CUDA_TRY(cudaEventRecord(c->ev_t[1], s));
     const MultiResult res = *c->host_result;
     c->last.n_in = n_local;
     c->last.n_out = res.n_out;
@@ -352,7 +426,7 @@ LSD_API int lsd_sort_multi(lsd_multi_ctx* c, const uint32_t* keys, uint64_t n_lo
     c->last.sent_bytes = 4 * res.sent;
     c->last.first_bucket = res.first_bucket;
     c->last.last_bucket = res.last_bucket;
-    c->last.exchange_digit = res.keep_local ? 0xFFFFFFFFu : res.digit;
+    c->last.exchange_shift = res.keep_local ? 0xFFFFFFFFu : res.shift;
     *n_out = res.n_out;
     if (res.overflow) {  // identical on every rank: all return the same status, nothing is moved
         *n_out = res.n_out_max;
@@ -364,7 +438,7 @@ LSD_API int lsd_sort_multi(lsd_multi_ctx* c, const uint32_t* keys, uint64_t n_lo
     if (res.keep_local) {  // all keys equal: nothing to exchange, the rank's keys are its slice
         if (n_local > 0) LSD_CUDA_TRY(cudaMemcpyAsync(c->recv, keys, sizeof(uint32_t) * n_local, cudaMemcpyDeviceToDevice, s));
     } else {
-        rc = pass_enqueue(keys, nullptr, n_local, c->r, (int)res.digit, 0, sort_ws, c->sort_ws_bytes, nullptr, s, dst, seg, abort_flag);
+        rc = pass_enqueue(keys, nullptr, n_local, c->r, 0, 0, sort_ws, c->sort_ws_bytes, nullptr, s, dst, seg, abort_flag, (int)res.shift);
         if (rc != LSD_OK) return rc;
     }
     if (comm.barrier(comm.ctx, stream) != 0) return LSD_ERR_COMM;

@@ -190,9 +190,15 @@ onesweep_lpc32_kernel(const PassArgs a)
     }
     char* mat_bytes = reinterpret_cast<char*>(s_mat);
     const uint32_t lane4 = lane << 2;
+    // SHIFT < 0: the digit position is a run-time value (the exchange window of lsd_sort_multi: any 8 bits of the key)
+    const int shift = SHIFT >= 0 ? SHIFT : a.shift;
+    auto cell_of = [&](uint32_t k) -> uint32_t {
+        if constexpr (SHIFT >= 0) return cell_offset<RB, SHIFT < 0 ? 0 : SHIFT>(k, lane4);
+        else return (((k >> shift) & (uint32_t)(H - 1)) << 7) | lane4;
+    };
 #pragma unroll
     for (int i = 0; i < ITEMS; ++i)
-        atomicAdd(reinterpret_cast<uint32_t*>(mat_bytes + cell_offset<RB, SHIFT>(key[i], lane4)), 4u);
+        atomicAdd(reinterpret_cast<uint32_t*>(mat_bytes + cell_of(key[i])), 4u);
     if (warp == 0) LSD_TRACE(2);  // warp 0 issued its counts
     __syncthreads();  // counts complete; all keys are in registers: s_keys is now the reorder buffer
     if (warp == 0) LSD_TRACE(3);  // count barrier passed
@@ -413,7 +419,7 @@ onesweep_lpc32_kernel(const PassArgs a)
     // version is instruction-bound instead), so the form with the fewest instructions stays.
 #pragma unroll
     for (int i = 0; i < ITEMS; ++i) {
-        const uint32_t old = atomicAdd(reinterpret_cast<uint32_t*>(mat_bytes + cell_offset<RB, SHIFT>(key[i], lane4)), 4u);
+        const uint32_t old = atomicAdd(reinterpret_cast<uint32_t*>(mat_bytes + cell_of(key[i])), 4u);
         if (i & 1) rk[i >> 1] = __byte_perm(rk[i >> 1], old, 0x5410); else rk[i >> 1] = old;
     }
     if (warp + 1 < (uint32_t)WARPS) named_bar_arrive(warp + 1, 64);
@@ -474,7 +480,7 @@ onesweep_lpc32_kernel(const PassArgs a)
             uint32_t d = 0;
             if (p < valid) {
                 const uint32_t k = s_keys[p];
-                d = (k >> SHIFT) & (H - 1);
+                d = (k >> shift) & (H - 1);
                 st_key<5>(out + s_gbase[d] + p, TYPED ? key_from_unsigned(k, xout) : k);
             }
             if (i & 3) dpk[i >> 2] |= d << (8 * (i & 3)); else dpk[i >> 2] = d;
@@ -529,12 +535,12 @@ onesweep_lpc32_kernel(const PassArgs a)
         for (int i = 0; i < ITEMS; ++i) {
             const uint32_t p = i * THREADS + tid;
             const uint32_t k = s_keys[p];
-            st_key<CLR>(out + s_gbase[(k >> SHIFT) & (H - 1)] + p, k);
+            st_key<CLR>(out + s_gbase[(k >> shift) & (H - 1)] + p, k);
         }
     } else {
         for (uint32_t p = tid; p < valid; p += THREADS) {
             const uint32_t k = s_keys[p];
-            out[s_gbase[(k >> SHIFT) & (H - 1)] + p] = TYPED ? key_from_unsigned(k, xout) : k;
+            out[s_gbase[(k >> shift) & (H - 1)] + p] = TYPED ? key_from_unsigned(k, xout) : k;
         }
     }
     if (warp == 0) LSD_TRACE(12);  // warp 0 issued its stores
@@ -563,6 +569,9 @@ int onesweep_lpc32_launch(const PassArgs& a, cudaStream_t s)
         case 16: return onesweep_lpc32_launch_shift<RB, WARPS, ITEMS, MINB, 16, LB, CLR, MODE, SP>(a, s);
         case 24: return onesweep_lpc32_launch_shift<RB, WARPS, ITEMS, MINB, 24, LB, CLR, MODE, SP>(a, s);
     }
+    // any other digit position: the run-time form, built for the peer-scatter pass only (exchange window of lsd_sort_multi)
+    if constexpr (MODE == kPassPeer)
+        if (a.shift > 0 && a.shift < 24) return onesweep_lpc32_launch_shift<RB, WARPS, ITEMS, MINB, -1, LB, CLR, MODE, SP>(a, s);
     return LSD_ERR_INVALID_VALUE;
 }
 

@@ -280,13 +280,14 @@ single_pass_plan_kernel(const uint64_t* __restrict__ hist, uint64_t* __restrict_
 
 int pass_enqueue(const uint32_t* in, uint32_t* out, uint64_t n, int r, int bit_group, int block, void* ws,
                  size_t ws_bytes, uint64_t* hist_out, cudaStream_t s, const uint64_t* dst_ptrs, const uint32_t* dst_seg,
-                 const uint32_t* abort_flag)
+                 const uint32_t* abort_flag, int peer_shift)
 {
     SortLayout L;
     const int st = make_layout(n, r, block, nullptr, &L);
     if (st != LSD_OK) return st;
     if (bit_group < 0 || bit_group >= L.passes) return LSD_ERR_INVALID_VALUE;
     const bool peer = dst_ptrs != nullptr;
+    if (peer_shift >= 0 && (!peer || peer_shift + r > 32)) return LSD_ERR_INVALID_VALUE;
     if (peer && !L.k->launch_peer) return LSD_ERR_UNSUPPORTED;
     if (n == 0) {
         if (hist_out) LSD_CUDA_TRY(cudaMemsetAsync(hist_out, 0, sizeof(uint64_t) * L.H, s));
@@ -328,7 +329,7 @@ int pass_enqueue(const uint32_t* in, uint32_t* out, uint64_t n, int r, int bit_g
         a.portion_keys = pkeys;
         a.tiles = (pkeys + L.k->tile - 1) / L.k->tile;
         a.pass = bit_group;
-        a.shift = bit_group * r;
+        a.shift = peer_shift >= 0 ? peer_shift : bit_group * r;  // peer-scatter: the digit may sit at any bit position
         a.trace = nullptr;
         a.dst_ptrs = dst_ptrs;
         a.dst_seg = dst_seg;

@@ -29,7 +29,8 @@ int sort_enqueue(uint32_t* keys, uint32_t* scratch, uint64_t n, int r, int block
 // abort_flag (device, optional): the pass exits at once if *abort_flag != 0 when its plan kernel runs.
 int pass_enqueue(const uint32_t* in, uint32_t* out, uint64_t n, int r, int bit_group, int block, void* ws,
                  size_t ws_bytes, uint64_t* hist_out, cudaStream_t s, const uint64_t* dst_ptrs = nullptr,
-                 const uint32_t* dst_seg = nullptr, const uint32_t* abort_flag = nullptr);
+                 const uint32_t* dst_seg = nullptr, const uint32_t* abort_flag = nullptr, int peer_shift = -1);
+// peer_shift >= 0 (peer-scatter mode only): the digit is bits [peer_shift, peer_shift + r) instead of digit `bit_group`
 
 // Composite digit widths (r in 3..16 other than 4, 8): one pass as sub-passes of the 8-bit kernel; per-digit histograms.
 size_t wide_pass_workspace_bytes(uint64_t n);

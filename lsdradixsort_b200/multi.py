@@ -15,8 +15,9 @@ Rank r ends with the r-th slice of the globally sorted sequence.  Two exchanges:
 * ``MultiSorter`` (default, ``distributed_sort(..., peer=...)``): a caller of the C ABI's ``lsd_sort_multi``
   (include/lsdsort.h, csrc/multi.cu).  Steps 2-4 are planned on the device and executed by ONE pass kernel that stores
   every bucket straight into its owner's receive buffer over NVLink peer memory; torch.distributed only supplies the two
-  collectives (an 8 KiB all-gather, a barrier) as callbacks.  It partitions on the highest digit that VARIES over the
-  input (keys below 2^24 / 2^16 / 2^8 are balanced over their own top byte; all-equal keys stay where they are).
+  collectives (an 8 KiB all-gather, a barrier) as callbacks.  It partitions on the 8-bit window that ends at the highest
+  bit that VARIES over the input (keys in any narrow range are balanced over their own 8 most significant varying bits;
+  all-equal keys stay where they are).
 * the NCCL path (``peer=None``): ``lsd_sort_pass`` + ``all_to_all_single`` with the plan computed on the host with numpy.
   Kept as the parity reference for the fused path and for the CPU (gloo) tests of the host logic, which replace the
   device steps by a test double.
@@ -171,7 +172,7 @@ class MultiSorter:
         owns = ms.first_bucket <= ms.last_bucket
         stats = ExchangeStats(int(ms.n_in), int(ms.n_out), int(ms.sent_bytes), 0,
                               int(ms.first_bucket) if owns else -1, int(ms.last_bucket) if owns else -1)
-        stats.exchange_digit = None if ms.exchange_digit == 0xFFFFFFFF else int(ms.exchange_digit)
+        stats.exchange_shift = None if ms.exchange_shift == 0xFFFFFFFF else int(ms.exchange_shift)
         if timing:
             stats.stage_ms_direct = {"hist_allgather_plan": float(ms.plan_ms), "partition": float(ms.exchange_ms),
                                      "all_to_all": 0.0, "local_sort": float(ms.sort_ms)}
@@ -225,7 +226,7 @@ class ExchangeStats:
     owner_first_bucket: int
     owner_last_bucket: int
     events: Optional[list] = None  # CUDA events between the stages when timing was requested
-    exchange_digit: Optional[int] = 3  # digit the exchange partitioned on (lsd_sort_multi: the highest one that varies; None = all keys equal)
+    exchange_shift: Optional[int] = 24  # the exchange partitioned on bits [shift, shift + 8) (lsd_sort_multi: the window that ends at the highest varying bit; None = all keys equal)
     stage_ms_direct: Optional[dict] = None  # lsd_sort_multi reports the stage times itself
 
     def stage_ms(self) -> dict:

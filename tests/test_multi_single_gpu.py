@@ -77,7 +77,7 @@ def _rank_main(rank, comm, keys_np, capacity, results, errors):
         comm.bar.wait()  # nobody unmaps while a peer may still be writing
         results[rank] = (st, int(n_out.value), recv[: int(n_out.value)].cpu().numpy().view(np.uint32).copy() if st == 0 else None,
                          bool((recv == 0x5A5A5A5A).all()) if st != 0 else None,
-                         (int(ms.first_bucket), int(ms.last_bucket), int(ms.n_out_max), int(ms.exchange_digit)))
+                         (int(ms.first_bucket), int(ms.last_bucket), int(ms.n_out_max), int(ms.exchange_shift)))
         lib.lsd_multi_ctx_destroy(ctx)
     except Exception as e:  # noqa: BLE001
         errors.append((rank, repr(e)))
@@ -87,9 +87,20 @@ def _rank_main(rank, comm, keys_np, capacity, results, errors):
             pass
 
 
+def _expected_shift(keys):
+    """The exchange window of lsd_sort_multi: the 8 bits that end at the highest bit in which the keys differ."""
+    allk = np.concatenate(keys)
+    differ = int(np.bitwise_or.reduce(allk)) & ~int(np.bitwise_and.reduce(allk))
+    return max(0, differ.bit_length() - 1 - 7)
+
+
 def _keys(kind, n, seed):
-    if kind == "small_range":     # keys below 2^12: digits 3 and 2 are constant, the exchange partitions on digit 1
+    if kind == "small_range":     # keys below 2^12: the window is bits [4, 12) -- it straddles digits 0 and 1
         return (keygen.make_keys("uniform", n, seed) & np.uint32(0xFFF)).astype(np.uint32)
+    if kind == "range17":         # keys below 2^17: the top-digit histogram is one bucket, digit 2 has two
+        return (keygen.make_keys("uniform", n, seed) & np.uint32(0x1FFFF)).astype(np.uint32)
+    if kind == "offset_range":    # 1000 values next to 2^31: the constant high bits are not zero
+        return (np.uint32(0x80000000) + keygen.make_keys("uniform", n, seed) % np.uint32(1000)).astype(np.uint32)
     if kind == "heavy_bucket":    # 90 % of the keys share one top-digit bucket: a rank's share exceeds any sane slack
         u = keygen.make_keys("uniform", n, seed)
         return np.where(u % np.uint32(10) != 0, u & np.uint32(0x00FFFFFF), u).astype(np.uint32)
@@ -119,13 +130,12 @@ def test_sort_multi_threads_on_one_gpu(world, kind):
     assert np.array_equal(np.concatenate([r[2] for r in results]), whole)  # rank order == global order
     assert sum(r[1] for r in results) == whole.size
     # the device-side plan is the map the host-side numpy plan derives (multi.assign_buckets) from the histogram of the
-    # highest digit that varies (the top one unless the keys are small: "sorted" at this size stays below 2^24)
-    allk = np.concatenate(keys)
-    digit = max(p for p in range(4) if np.unique((allk >> np.uint32(8 * p)) & np.uint32(255)).size > 1)
-    per_rank = np.stack([np.bincount((k >> np.uint32(8 * digit)) & np.uint32(255), minlength=256) for k in keys]).astype(np.int64)
+    # exchange window (the top digit unless the keys are small: "sorted" at this size stays below 2^22)
+    shift = _expected_shift(keys)
+    per_rank = np.stack([np.bincount((k >> np.uint32(shift)) & np.uint32(255), minlength=256) for k in keys]).astype(np.int64)
     owner = multi.assign_buckets(per_rank.sum(axis=0), world)
     for r, res in enumerate(results):
-        assert res[4][3] == digit
+        assert res[4][3] == shift
         mine = np.nonzero(owner == r)[0]
         if mine.size:
             assert res[4][0] == int(mine[0]) and res[4][1] == int(mine[-1])
@@ -135,14 +145,15 @@ def test_sort_multi_threads_on_one_gpu(world, kind):
 
 
 @pytest.mark.parametrize("world", [2, 4])
-@pytest.mark.parametrize("kind,digit", [("low_nibble", 0), ("small_range", 1)])
-def test_sort_multi_partitions_on_the_highest_varying_digit(world, kind, digit):
-    """BASELINE config 4 x config 5: keys whose top digits are constant are balanced over the highest digit that varies
-    instead of landing on one rank -- the ordinary 25 % slack is enough."""
+@pytest.mark.parametrize("kind,shift", [("low_nibble", 0), ("small_range", 4), ("range17", 9), ("offset_range", 2)])
+def test_sort_multi_partitions_on_the_most_significant_varying_bits(world, kind, shift):
+    """BASELINE config 4 x config 5: keys that live in a narrow range are balanced over the 8-bit window that ends at the
+    highest bit in which they differ instead of landing on one rank -- the ordinary 25 % slack is enough."""
     n_local = 150_000 + world
     keys, results = _run(world, kind, n_local, capacity=int(n_local * 1.25) + 64)
+    assert _expected_shift(keys) == shift
     assert all(r[0] == N.LSD_OK for r in results), [r[0] for r in results]
-    assert all(r[4][3] == digit for r in results)
+    assert all(r[4][3] == shift for r in results)
     whole = np.sort(np.concatenate(keys))
     assert np.array_equal(np.concatenate([r[2] for r in results]), whole)
     shares = [r[1] for r in results]
