@@ -3,7 +3,7 @@
 // for everything else.  Checks the result against std::sort of the union of all ranks' keys and prints per-stage device
 // times.  Harness only: nothing here is on the product path.
 //
-//     lsd_multi_check [--gpus N] [--log2n K (keys per rank)] [--kind uniform|sorted|equal] [--reps R]
+//     lsd_multi_check [--gpus N] [--log2n K (keys per rank)] [--kind uniform|sorted|equal|nibble|range17|offset] [--reps R]
 #include <algorithm>
 #include <atomic>
 #include <cstdint>
@@ -40,9 +40,13 @@ static uint32_t hash32(uint64_t x)
 static void make_keys(std::vector<uint32_t>& k, const std::string& kind, int rank)
 {
     for (size_t i = 0; i < k.size(); ++i) {
+        const uint32_t u = hash32(((uint64_t)rank << 40) + i);
         if (kind == "sorted") k[i] = (uint32_t)(i * 7);
         else if (kind == "equal") k[i] = 0xDEADBEEFu;
-        else k[i] = hash32(((uint64_t)rank << 40) + i);
+        else if (kind == "nibble") k[i] = u & 0xFu;                  // BASELINE config 4: only the low nibble varies
+        else if (kind == "range17") k[i] = u & 0x1FFFFu;             // keys below 2^17: the exchange window straddles two digits
+        else if (kind == "offset") k[i] = 0x80000000u + u % 1000u;   // a thousand values next to 2^31
+        else k[i] = u;
     }
 }
 
@@ -64,7 +68,8 @@ int main(int argc, char** argv)
         return 2;
     }
     const uint64_t n_local = 1ull << log2n;
-    const uint64_t capacity = kind == "uniform" ? n_local + n_local / 4 + 65536 : n_local * gpus + 64;
+    // the ordinary 25 % slack for everything the exchange window balances; "sorted" ramps differ per rank count
+    const uint64_t capacity = kind == "sorted" ? n_local * gpus + 64 : n_local + n_local / 4 + 65536;
     std::vector<ncclComm_t> comms(gpus);
     std::vector<int> devs(gpus);
     for (int i = 0; i < gpus; ++i) devs[i] = i;
@@ -137,9 +142,9 @@ int main(int argc, char** argv)
     std::printf("-- lsd_sort_multi over the C ABI (threads + ncclCommInitAll) --\nGPUs: %d\nKeys per rank: %llu\nKind: %s\n", gpus,
                 (unsigned long long)n_local, kind.c_str());
     for (int r = 0; r < gpus; ++r)
-        std::printf("rank %d: owns %llu keys (buckets %u..%u), sent %.1f MB | plan %.3f ms, exchange %.3f ms, local sort %.3f ms\n", r,
-                    (unsigned long long)stats[r].n_out, stats[r].first_bucket, stats[r].last_bucket, stats[r].sent_bytes / 1e6,
-                    stats[r].plan_ms, stats[r].exchange_ms, stats[r].sort_ms);
+        std::printf("rank %d: owns %llu keys (buckets %u..%u of bits %d..%d), sent %.1f MB | plan %.3f ms, exchange %.3f ms, local sort %.3f ms\n", r,
+                    (unsigned long long)stats[r].n_out, stats[r].first_bucket, stats[r].last_bucket, (int)stats[r].exchange_shift,
+                    (int)stats[r].exchange_shift + 7, stats[r].sent_bytes / 1e6, stats[r].plan_ms, stats[r].exchange_ms, stats[r].sort_ms);
     std::printf("%s\n", ok ? "CHECK PASSED: concatenated rank slices == std::sort of all keys" : "CHECK FAILED");
     return ok ? 0 : 1;
 }
