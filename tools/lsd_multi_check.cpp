@@ -142,9 +142,15 @@ int main(int argc, char** argv)
     std::printf("-- lsd_sort_multi over the C ABI (threads + ncclCommInitAll) --\nGPUs: %d\nKeys per rank: %llu\nKind: %s\n", gpus,
                 (unsigned long long)n_local, kind.c_str());
     for (int r = 0; r < gpus; ++r)
-        std::printf("rank %d: owns %llu keys (buckets %u..%u of bits %d..%d), sent %.1f MB | plan %.3f ms, exchange %.3f ms, local sort %.3f ms\n", r,
-                    (unsigned long long)stats[r].n_out, stats[r].first_bucket, stats[r].last_bucket, (int)stats[r].exchange_shift,
-                    (int)stats[r].exchange_shift + 7, stats[r].sent_bytes / 1e6, stats[r].plan_ms, stats[r].exchange_ms, stats[r].sort_ms);
+    {
+        char where[64];
+        if (stats[r].exchange_shift == 0xFFFFFFFFu) std::snprintf(where, sizeof(where), "all keys equal: nothing exchanged");
+        else std::snprintf(where, sizeof(where), "buckets %u..%u of bits %u..%u", stats[r].first_bucket, stats[r].last_bucket,
+                           stats[r].exchange_shift, stats[r].exchange_shift + 7);
+        std::printf("rank %d: owns %llu keys (%s), sent %.1f MB | plan %.3f ms, exchange %.3f ms, local sort %.3f ms\n", r,
+                    (unsigned long long)stats[r].n_out, where, stats[r].sent_bytes / 1e6, stats[r].plan_ms, stats[r].exchange_ms,
+                    stats[r].sort_ms);
+    }
     std::printf("%s\n", ok ? "CHECK PASSED: concatenated rank slices == std::sort of all keys" : "CHECK FAILED");
     return ok ? 0 : 1;
 }
