@@ -179,7 +179,9 @@ scan_kernel(uint32_t* __restrict__ a, uint64_t n, ScanWorkspace* __restrict__ ws
 // the barrier behind the look-back, 3.5 TB/s.  Here the tile lands in shared memory (16 KiB per 128-thread CTA),
 // the threads only keep 8 running sums across the wait (~40 registers), and re-read their vectors from shared
 // memory once the tile prefix is known: 12-13 CTAs per SM are in flight, which is what the HBM latency x bandwidth
-// product of B200 needs.
+// product of B200 needs.  Round 2: every CTA also pulls the tile that will be drawn 12 MiB of tickets later into L2
+// (cp.async.bulk.prefetch.L2), so a tile's own load is an L2 round trip instead of a DRAM access under full load (the
+// trace had the tile land 6.6 K cycles after the ticket): 0.505 -> 0.427 ms at 2^28 = 5.03 TB/s, 0.77 of the copy roofline.
 // -------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t scan_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -193,7 +195,8 @@ __device__ __forceinline__ uint4 lds128_volatile(const uint32_t* p)
 // TRACE: phase clocks per tile (LSD_SCAN_TRACE=1); compile-time so that the shipped kernel carries no run-time checks
 template <int THREADS, bool TRACE = false>
 __global__ void __launch_bounds__(THREADS)
-scan_tma_kernel(uint32_t* __restrict__ a, uint64_t n, ScanWorkspace* __restrict__ ws, uint32_t* __restrict__ trace)
+scan_tma_kernel(uint32_t* __restrict__ a, uint64_t n, ScanWorkspace* __restrict__ ws, uint32_t* __restrict__ trace,
+                uint32_t prefetch_tiles)
 {
     const long long t_start = (TRACE && trace) ? clock64() : 0;
 #define SCAN_TRACE(slot) do { if constexpr (TRACE) if (trace && tid == 0) trace[(size_t)tile * 8 + (slot)] = (uint32_t)(clock64() - t_start); } while (0)
@@ -221,6 +224,13 @@ scan_tma_kernel(uint32_t* __restrict__ a, uint64_t n, ScanWorkspace* __restrict_
         if constexpr (TRACE)
             if (trace) trace[(size_t)t * 8 + 0] = (uint32_t)(clock64() - t_start);
         const uint64_t b = (uint64_t)t * TILE;
+        // pull the tile that will be drawn `prefetch_tiles` tickets from now into L2: a tile's own load then costs an L2
+        // round trip instead of a DRAM access under full load (the trace had the tile land 6.6 K cycles after the ticket)
+        if (prefetch_tiles != 0u) {
+            const uint64_t pf = ((uint64_t)t + prefetch_tiles) * TILE;
+            if (pf < n && n - pf >= (uint64_t)TILE)
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a + pf), "r"(TILE * 4) : "memory");
+        }
         if (n - b >= (uint64_t)TILE) {
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(scan_smem_u32(&s_bar)), "r"(TILE * 4) : "memory");
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -686,7 +696,16 @@ static int scan_threads_for(int block)
 
 // LSD_SCAN_TRACE=1 (tuning aid): 8 uint32 phase clocks per tile are written after the tile states
 static const bool g_scan_l2 = scan_env("LSD_SCAN_L2");
-static const bool g_scan_trace = scan_env("LSD_SCAN_TRACE");
+// L2 prefetch distance of scan_tma_kernel in BYTES (0 = off).  Measured at 2^28 (profiles/r02_scan_l2_prefetch.jsonl, first
+// sweep in tiles, second in MiB): off 0.505-0.517 ms; 6 / 8 / 12 / 16 / 20 / 24 MiB ahead 0.437 / 0.431 / 0.427 / 0.433 / 0.445 /
+// 0.456 ms; 32 MiB 0.50; 64 MiB 0.59 (the lines are evicted before their tile comes up).  12 MiB is at or next to the best
+// distance for all three tile sizes (block 128 / 256 / 512) and at 2^30 (1.670 ms = 5.14 TB/s against 2.010 ms).
+#ifdef LSD_TUNING_VARIANTS
+static uint32_t g_scan_prefetch_bytes = 12u << 20;
+extern "C" __attribute__((visibility("default"))) void lsd_debug_scan_prefetch(int bytes) { g_scan_prefetch_bytes = (uint32_t)bytes; }
+#else
+static constexpr uint32_t g_scan_prefetch_bytes = 12u << 20;
+#endif
 
 size_t scan_workspace_bytes(uint64_t n, int block)
 {
@@ -744,29 +763,29 @@ int launch_prefix_sum(uint32_t* a, uint64_t n, int block, void* ws, size_t ws_by
             case 128:
                 if (trace) {
                     LSD_CUDA_TRY(cudaFuncSetAttribute(scan_tma_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                    scan_tma_kernel<128, true><<<(unsigned)tiles, 128, smem, s>>>(a, n, w, trace);
+                    scan_tma_kernel<128, true><<<(unsigned)tiles, 128, smem, s>>>(a, n, w, trace, g_scan_prefetch_bytes / (uint32_t)(tile * sizeof(uint32_t)));
                     break;
                 }
                 LSD_CUDA_TRY(cudaFuncSetAttribute(scan_tma_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                scan_tma_kernel<128><<<(unsigned)tiles, 128, smem, s>>>(a, n, w, trace);
+                scan_tma_kernel<128><<<(unsigned)tiles, 128, smem, s>>>(a, n, w, trace, g_scan_prefetch_bytes / (uint32_t)(tile * sizeof(uint32_t)));
                 break;
             case 256:
                 if (trace) {
                     LSD_CUDA_TRY(cudaFuncSetAttribute(scan_tma_kernel<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                    scan_tma_kernel<256, true><<<(unsigned)tiles, 256, smem, s>>>(a, n, w, trace);
+                    scan_tma_kernel<256, true><<<(unsigned)tiles, 256, smem, s>>>(a, n, w, trace, g_scan_prefetch_bytes / (uint32_t)(tile * sizeof(uint32_t)));
                     break;
                 }
                 LSD_CUDA_TRY(cudaFuncSetAttribute(scan_tma_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                scan_tma_kernel<256><<<(unsigned)tiles, 256, smem, s>>>(a, n, w, trace);
+                scan_tma_kernel<256><<<(unsigned)tiles, 256, smem, s>>>(a, n, w, trace, g_scan_prefetch_bytes / (uint32_t)(tile * sizeof(uint32_t)));
                 break;
             default:
                 if (trace) {
                     LSD_CUDA_TRY(cudaFuncSetAttribute(scan_tma_kernel<512, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                    scan_tma_kernel<512, true><<<(unsigned)tiles, 512, smem, s>>>(a, n, w, trace);
+                    scan_tma_kernel<512, true><<<(unsigned)tiles, 512, smem, s>>>(a, n, w, trace, g_scan_prefetch_bytes / (uint32_t)(tile * sizeof(uint32_t)));
                     break;
                 }
                 LSD_CUDA_TRY(cudaFuncSetAttribute(scan_tma_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                scan_tma_kernel<512><<<(unsigned)tiles, 512, smem, s>>>(a, n, w, trace);
+                scan_tma_kernel<512><<<(unsigned)tiles, 512, smem, s>>>(a, n, w, trace, g_scan_prefetch_bytes / (uint32_t)(tile * sizeof(uint32_t)));
                 break;
         }
     } else {
