@@ -706,6 +706,7 @@ extern "C" __attribute__((visibility("default"))) void lsd_debug_scan_prefetch(i
 #else
 static constexpr uint32_t g_scan_prefetch_bytes = 12u << 20;
 #endif
+static const bool g_scan_trace = scan_env("LSD_SCAN_TRACE");
 
 size_t scan_workspace_bytes(uint64_t n, int block)
 {
