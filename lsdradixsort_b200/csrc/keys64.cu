@@ -35,16 +35,19 @@ __host__ __device__ __forceinline__ uint64_t key64_from_unsigned(uint64_t u, uin
 
 constexpr int kSplitThreads = 256;
 
-// lo / hi: m entries each; tail: the n - m keys behind them (unsigned images, ascending)
+// lo / hi: m entries each (m % 4 == 0); tail: the n - m keys behind them (unsigned images, ascending).
+// Two keys per thread and step: one 128-bit load, two 64-bit stores.
 __global__ void __launch_bounds__(kSplitThreads)
 split64_kernel(const uint64_t* __restrict__ keys, uint32_t* __restrict__ lo, uint32_t* __restrict__ hi, uint64_t m, uint64_t n,
                uint64_t* __restrict__ tail, uint32_t key_type)
 {
     const uint64_t stride = (uint64_t)gridDim.x * kSplitThreads;
-    for (uint64_t i = (uint64_t)blockIdx.x * kSplitThreads + threadIdx.x; i < m; i += stride) {
-        const uint64_t u = key64_to_unsigned(__ldcs(keys + i), key_type);
-        lo[i] = (uint32_t)u;
-        hi[i] = (uint32_t)(u >> 32);
+    const uint64_t pairs = m >> 1;
+    for (uint64_t i = (uint64_t)blockIdx.x * kSplitThreads + threadIdx.x; i < pairs; i += stride) {
+        const ulonglong2 k = __ldcs(reinterpret_cast<const ulonglong2*>(keys) + i);
+        const uint64_t u0 = key64_to_unsigned(k.x, key_type), u1 = key64_to_unsigned(k.y, key_type);
+        reinterpret_cast<uint2*>(lo)[i] = make_uint2((uint32_t)u0, (uint32_t)u1);
+        reinterpret_cast<uint2*>(hi)[i] = make_uint2((uint32_t)(u0 >> 32), (uint32_t)(u1 >> 32));
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         uint64_t t[3] = {~0ull, ~0ull, ~0ull};
@@ -59,7 +62,8 @@ split64_kernel(const uint64_t* __restrict__ keys, uint32_t* __restrict__ lo, uin
 }
 
 // Two-way merge of the m sorted (hi, lo) keys with the <= 3 sorted tail keys: main key i goes to i + #{tail < key},
-// tail key j to j + #{main <= tail_j} (ties: main first; equal 64-bit keys are indistinguishable).
+// tail key j to j + #{main <= tail_j} (ties: main first; equal 64-bit keys are indistinguishable).  Two keys per thread
+// and step; without a tail (n % 4 == 0) they leave as one 128-bit store.
 __global__ void __launch_bounds__(kSplitThreads)
 merge64_kernel(uint64_t* __restrict__ keys, const uint32_t* __restrict__ lo, const uint32_t* __restrict__ hi, uint64_t m, uint64_t n,
                const uint64_t* __restrict__ tail, uint32_t key_type)
@@ -67,10 +71,19 @@ merge64_kernel(uint64_t* __restrict__ keys, const uint32_t* __restrict__ lo, con
     const uint32_t cnt = (uint32_t)(n - m);
     const uint64_t t0 = cnt > 0 ? tail[0] : 0, t1 = cnt > 1 ? tail[1] : 0, t2 = cnt > 2 ? tail[2] : 0;
     const uint64_t stride = (uint64_t)gridDim.x * kSplitThreads;
-    for (uint64_t i = (uint64_t)blockIdx.x * kSplitThreads + threadIdx.x; i < m; i += stride) {
-        const uint64_t u = ((uint64_t)__ldcs(hi + i) << 32) | __ldcs(lo + i);
-        const uint32_t before = (cnt > 0 && t0 < u ? 1u : 0u) + (cnt > 1 && t1 < u ? 1u : 0u) + (cnt > 2 && t2 < u ? 1u : 0u);
-        keys[i + before] = key64_from_unsigned(u, key_type);
+    const uint64_t pairs = m >> 1;
+    for (uint64_t i = (uint64_t)blockIdx.x * kSplitThreads + threadIdx.x; i < pairs; i += stride) {
+        const uint2 l = __ldcs(reinterpret_cast<const uint2*>(lo) + i);
+        const uint2 h = __ldcs(reinterpret_cast<const uint2*>(hi) + i);
+        const uint64_t u0 = ((uint64_t)h.x << 32) | l.x, u1 = ((uint64_t)h.y << 32) | l.y;
+        if (cnt == 0) {
+            reinterpret_cast<ulonglong2*>(keys)[i] = make_ulonglong2(key64_from_unsigned(u0, key_type), key64_from_unsigned(u1, key_type));
+        } else {
+            const uint32_t b0 = (t0 < u0 ? 1u : 0u) + (cnt > 1 && t1 < u0 ? 1u : 0u) + (cnt > 2 && t2 < u0 ? 1u : 0u);
+            const uint32_t b1 = (t0 < u1 ? 1u : 0u) + (cnt > 1 && t1 < u1 ? 1u : 0u) + (cnt > 2 && t2 < u1 ? 1u : 0u);
+            keys[2 * i + b0] = key64_from_unsigned(u0, key_type);
+            keys[2 * i + 1 + b1] = key64_from_unsigned(u1, key_type);
+        }
     }
     if (blockIdx.x == 0 && threadIdx.x < cnt) {
         const uint64_t t = tail[threadIdx.x];
@@ -113,7 +126,7 @@ int sort64_enqueue(uint64_t* keys, uint64_t* scratch, uint64_t n, uint32_t key_t
     uint32_t* pp1 = pp0 + m;
     uint64_t* tail = reinterpret_cast<uint64_t*>(static_cast<char*>(ws) + pairs_ws);
 
-    const uint64_t want = (m + kSplitThreads - 1) / kSplitThreads;
+    const uint64_t want = ((m >> 1) + kSplitThreads - 1) / kSplitThreads;
     const uint64_t cap = (uint64_t)sm_count() * 16;
     const int grid = (int)(want < 1 ? 1 : (want < cap ? want : cap));
     split64_kernel<<<grid, kSplitThreads, 0, s>>>(keys, lo, hi, m, n, tail, key_type);
