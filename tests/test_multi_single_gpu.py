@@ -185,3 +185,22 @@ def test_sort_multi_larger_uniform_two_ranks():
     keys, results = _run(world, "uniform", n_local, capacity=int(n_local * 1.25))
     assert all(r[0] == N.LSD_OK for r in results)
     assert np.array_equal(np.concatenate([r[2] for r in results]), np.sort(np.concatenate(keys)))
+
+
+def test_sort_multi_ragged_and_empty_ranks():
+    """Ranks bring different numbers of keys, one of them none at all."""
+    world = 3
+    sizes = [100_003, 0, 41_000]
+    comm = ThreadComm(world)
+    keys = [keygen.make_keys("uniform", sizes[r], seed=70 + r) for r in range(world)]
+    results, errors = [None] * world, []
+    threads = [threading.Thread(target=_rank_main, args=(r, comm, keys[r], 200_000, results, errors)) for r in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(300)
+    assert not errors, errors
+    assert all(r[0] == N.LSD_OK for r in results)
+    assert np.array_equal(np.concatenate([r[2] for r in results]), np.sort(np.concatenate(keys)))
+    shares = [r[1] for r in results]
+    assert sum(shares) == sum(sizes) and max(shares) - min(shares) < 0.05 * sum(sizes)  # balanced over the ranks, not the sources
