@@ -50,6 +50,34 @@ __global__ void __launch_bounds__(THREADS) skeleton(const uint32_t* __restrict__
     }
     __syncthreads();
     asm volatile("{\n.reg .pred p;\nW_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n@p bra D_%=;\nbra W_%=;\nD_%=:\n}\n" ::"r"(smem_u32(&bar)) : "memory");
+    if (MODE >= 6) {
+        // 6: one thread per bucket: the 16-byte aligned middle of its run leaves by ONE bulk (TMA) store shared -> global (no
+        //    LSU work), the <= 3 words before and after it by scalar stores; 7: bulk stores only; 8: heads / tails only.
+        //    (Timing only: the source is taken at the 16-byte boundary next to the run, as if the reorder buffer had been laid
+        //    out with every run at its destination's alignment.)
+        const uint32_t bucket = tid;
+        const uint32_t s0 = tile_start(tile, bucket), s1 = tile_start(tile, bucket + 1);
+        const uint32_t mis = (bucket * 2654435761u >> 27);
+        uint32_t* dst = out + (size_t)bucket * stream_len + stream_pos(tile, bucket) + mis;
+        const uint32_t len = s1 - s0;
+        uint32_t head = (0u - (uint32_t)((unsigned long long)dst >> 2)) & 3u;
+        if (head > len) head = len;
+        const uint32_t mid = (len - head) & ~3u, tail = len - head - mid;
+        const uint32_t src = (s0 + head) & ~3u;
+        if (MODE != 8 && mid != 0u) {
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst + head), "r"(smem_u32(s + src)), "r"(mid * 4u) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        if (MODE != 7) {
+#pragma unroll
+            for (uint32_t j = 0; j < 3; ++j) {
+                if (j < head) dst[j] = s[s0 + j];
+                if (j < tail) dst[head + mid + j] = s[s0 + head + mid + j];
+            }
+        }
+        if (MODE != 8) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        return;
+    }
     if (MODE == 5) {
         // bucket-major copy-out: per-bucket info {start, length, destination} precomputed in shared memory (the pass kernel
         // has it there anyway); one warp store per (run, destination line): lanes = position inside the 128-byte line, so
@@ -156,6 +184,11 @@ int main()
                smem, t0, 8.0 * n / t0 / 1e6, t1, 8.0 * n / t1 / 1e6, t2, 8.0 * n / t2 / 1e6);
         printf("                  sector-misaligned runs %.3f ms | ragged runs, p-linear warps (pass kernels today) %.3f ms | ragged runs, line-aligned warps %.3f ms\n",
                t3, t4, t5);
+    }
+    for (size_t smem : {(size_t)TILE * 4 + 64, (size_t)70 * 1024}) {
+        const float t6 = run<6>(in, out, tiles, smem), t7 = run<7>(in, out, tiles, smem), t8 = run<8>(in, out, tiles, smem);
+        printf("smem/CTA %6zu B: ragged runs by bulk S2G stores + scalar heads/tails %.3f ms (%.0f GB/s) | bulk stores only %.3f ms | heads/tails only %.3f ms\n",
+               smem, t6, 8.0 * n / t6 / 1e6, t7, t8);
     }
     {   // in-place variant of the full-line copy (what an in-place scan does to DRAM: read and write streams share pages)
         const float t_in = run<0>(in, in, tiles, (size_t)TILE * 4);
