@@ -14,6 +14,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--log2n", type=int, default=28)
 ap.add_argument("--variant", type=int, default=19)
 ap.add_argument("--tile", type=int, default=8352)
+ap.add_argument("--r", type=int, default=8)
 ap.add_argument("--family", type=str, default="lpc", choices=["lpc", "cpc", "cpcp", "wide"])
 args = ap.parse_args()
 n = 1 << args.log2n
@@ -21,7 +22,7 @@ g = torch.Generator(device="cuda").manual_seed(0)
 src = torch.randint(-(2**31), 2**31, (n,), dtype=torch.int64, device="cuda", generator=g).to(torch.int32)
 tiles = (n + args.tile - 1) // args.tile
 trace = torch.zeros(tiles * 16, dtype=torch.int64, device="cuda")
-s = L.Sorter(n, r=8, variant=args.variant, debug_trace=trace.data_ptr())
+s = L.Sorter(n, r=args.r, variant=args.variant, debug_trace=trace.data_ptr())
 for _ in range(2):
     work = src.clone()
     trace.zero_()

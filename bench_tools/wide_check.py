@@ -21,6 +21,7 @@ ap.add_argument("--no-typed", action="store_true", help="skip the f32 / i32 chec
 ap.add_argument("--log2n", type=int, default=28)
 ap.add_argument("--reps", type=int, default=5)
 ap.add_argument("--skip-check", action="store_true")
+ap.add_argument("--r", type=int, default=8)
 args = ap.parse_args()
 variants = [int(x) for x in args.variants.split(",")]
 
@@ -42,7 +43,7 @@ if not args.skip_check:
                 keys = keygen.make_keys(kind, n, seed=v)
                 d = torch.from_numpy(keys.view(np.int32)).cuda()
                 try:
-                    L.sort_(d, r=8, variant=v)
+                    L.sort_(d, r=args.r, variant=v)
                 except Exception as e:  # noqa: BLE001
                     print(json.dumps({"variant": v, "kind": kind, "n": n, "error": str(e)}), flush=True)
                     bad += 1
@@ -56,13 +57,13 @@ if not args.skip_check:
         # multi-portion hand-off, typed keys, large uniform vs torch.sort
         keys = keygen.make_keys("entropy4_table", 150_001, seed=5)
         d = torch.from_numpy(keys.view(np.int32)).cuda()
-        L.sort_(d, r=8, variant=v, portion_keys=40000)
+        L.sort_(d, r=args.r, variant=v, portion_keys=40000)
         if not np.array_equal(d.cpu().numpy().view(np.uint32), np.sort(keys)):
             bad += 1
             print(json.dumps({"variant": v, "portions": "MISMATCH"}), flush=True)
         big = gpu_keys(1 << 26, v)
         want = usort(big)
-        L.sort_(big, r=8, variant=v)
+        L.sort_(big, r=args.r, variant=v)
         if not bool((big == want).all()):
             bad += 1
             print(json.dumps({"variant": v, "n": 1 << 26, "MISMATCH": True}), flush=True)
@@ -72,13 +73,13 @@ if not args.skip_check:
             continue
         f = torch.nan_to_num(gpu_keys(3_000_001, v + 1).view(torch.float32), nan=1.0)
         want_f = torch.sort(f).values
-        L.sort_(f, r=8, variant=v)
+        L.sort_(f, r=args.r, variant=v)
         if not bool((f == want_f).all()):
             bad += 1
             print(json.dumps({"variant": v, "f32": "MISMATCH"}), flush=True)
         i = gpu_keys(2_000_003, v + 2)
         want_i = torch.sort(i).values
-        L.sort_(i, r=8, variant=v, key_type="i32")
+        L.sort_(i, r=args.r, variant=v, key_type="i32")
         if not bool((i == want_i).all()):
             bad += 1
             print(json.dumps({"variant": v, "i32": "MISMATCH"}), flush=True)
@@ -91,7 +92,7 @@ work = torch.empty_like(src)
 want = usort(src) if not args.skip_check else None
 for v in variants:
     try:
-        s = L.Sorter(n, r=8, variant=v)
+        s = L.Sorter(n, r=args.r, variant=v)
     except Exception as e:  # noqa: BLE001
         print(json.dumps({"variant": v, "error": str(e)}))
         continue

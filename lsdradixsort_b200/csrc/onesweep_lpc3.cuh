@@ -12,6 +12,7 @@
 // digit shift is a run-time value (SHIFT < 0) to keep the number of instantiations down.
 #pragma once
 #include "onesweep_lpc32.cuh"
+#include "lookback_quad.cuh"
 
 namespace lsd {
 
@@ -55,6 +56,7 @@ onesweep_lpc3_kernel(const PassArgs a)
     static_assert(LBT >= H / 2, "one digit pair per look-back thread");
     constexpr bool PUB = CLR == 8;
     constexpr bool WALK2 = CLR == 9;  // pipelined look-back walk: next window in flight, whole-window fast path
+    constexpr bool QLB = CLR == 10;   // quad look-back (lookback_quad.cuh): 128-bit record accesses, the window spread over lanes
     static_assert(!PUB || (H == 256 && S_::OFF_HEADS + H + 4 - S_::OFF_DST >= 4 * H), "record copies live in the unused peer-scatter area");
     const int shift = SHIFT >= 0 ? SHIFT : a.shift;
     // run-time digits may be narrower than RB bits (sub-passes of the composite digit widths, sort.cu: pass_enqueue_wide)
@@ -267,6 +269,16 @@ onesweep_lpc3_kernel(const PassArgs a)
             named_bar_sync(kBarTot, (SW + LBW) * 32);
             if (warp == (uint32_t)WARPS - 1) LSD_TRACE(8);
             const uint32_t dt = tid - (uint32_t)(THREADS - LBT);
+            if constexpr (QLB) {
+                [[maybe_unused]] uint32_t q_rounds = 0, q_hops = 0;
+                lookback_quad_tile<H, LBW, LB>(a, lb_row, tile, warp - (uint32_t)(WARPS - LBW), lane, pads, dmask, s_tot, s_dp, s_gbase,
+                                               TRACE ? &q_rounds : nullptr, TRACE ? &q_hops : nullptr);
+                if constexpr (TRACE)
+                    if (a.trace && warp == (uint32_t)WARPS - 1 && lane == 0) {
+                        a.trace[(size_t)tile * 16 + 13] = q_rounds;
+                        a.trace[(size_t)tile * 16 + 14] = q_hops;
+                    }
+            } else
             if (dt < (uint32_t)H / 2) {
             const uint32_t cnt_lo = s_tot[2 * dt];
             uint32_t cnt_hi = s_tot[2 * dt + 1];

@@ -33,6 +33,7 @@ onesweep_lpc4_kernel(const PassArgs a)
     constexpr int IN_OFF = (S_::WORDS + 3) & ~3;               // else: a dedicated prefetch buffer behind everything
     static_assert(LBT >= H / 2, "one digit pair per look-back thread");
     static_assert(RB == 8, "8-bit digits only");
+    constexpr bool QLB = CLR == 10;  // quad look-back (lookback_quad.cuh)
     constexpr int EVEN = (WARPS + 1) / 2;  // warps of the even chain; they own the first EVEN*ITEMS keys of a lane segment
     static_assert(SW >= 2, "warps 0 and 1 (the heads of the two chains) are scan warps");
     static_assert(EVEN * ITEMS * 32 * 4 < 65536, "a row half must not carry into the other half");
@@ -248,6 +249,16 @@ onesweep_lpc4_kernel(const PassArgs a)
             named_bar_sync(kBarTot, (SW + LBW) * 32);
             if (warp == (uint32_t)WARPS - 1) LSD_TRACE(8);
             const uint32_t dt = tid - (uint32_t)(THREADS - LBT);
+            if constexpr (QLB) {
+                [[maybe_unused]] uint32_t q_rounds = 0, q_hops = 0;
+                lookback_quad_tile<H, LBW, LB>(a, lb_row, tile, warp - (uint32_t)(WARPS - LBW), lane, pads, (uint32_t)(H - 1), s_tot, s_dp,
+                                               s_gbase, TRACE ? &q_rounds : nullptr, TRACE ? &q_hops : nullptr);
+                if constexpr (TRACE)
+                    if (a.trace && warp == (uint32_t)WARPS - 1 && lane == 0) {
+                        a.trace[(size_t)tile * 16 + 13] = q_rounds;
+                        a.trace[(size_t)tile * 16 + 14] = q_hops;
+                    }
+            } else
             if (dt < (uint32_t)H / 2) {
             const uint32_t cnt_lo = s_tot[2 * dt];
             uint32_t cnt_hi = s_tot[2 * dt + 1];

@@ -10,6 +10,7 @@ static const OnesweepLauncher kTable[] = {
     make_launcher<2, 128, 16, kMatchBallot, true>(),
     make_launcher<2, 512, 16, kMatchBallot, true>(),
     make_launcher<2, 1024, 8, kMatchBallot, true>(),
+    make_lpc3_launcher<2, 9, 29, 3, 1, 10, 1, 0>(),       // 5: the default with the quad look-back (lookback_quad.cuh), 32 records per round
 #endif
 };
 

@@ -58,12 +58,7 @@ __device__ __forceinline__ void st_relaxed_gpu_v4(uint32_t* p, uint4 v)
 {
     asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
-__device__ __forceinline__ uint4 ld_relaxed_gpu_v4(const uint32_t* p)
-{
-    uint4 v;
-    asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
-    return v;
-}
+// ld_relaxed_gpu_v4: lookback_quad.cuh
 __device__ __forceinline__ void prefetch_l2_bulk(const void* p, uint32_t bytes)
 {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
