@@ -125,8 +125,9 @@ int sm_count();          // cached multiprocessor count of the current device
 int smem_optin_bytes();  // cached max opt-in shared memory per block
 
 // ---- entry points implemented per translation unit (called by api.cu) ----------------
+// zero_ptr / zero_bytes (16-byte granular, optional): memory the kernel zeroes on the side (the sort's look-back records)
 int launch_digit_histograms(const uint32_t* keys, uint64_t n, int r, uint64_t* hist, cudaStream_t s,
-                            uint32_t key_type = 0);
+                            uint32_t key_type = 0, void* zero_ptr = nullptr, size_t zero_bytes = 0);
 int launch_top_digit_histogram(const uint32_t* keys, uint64_t n, int r, uint64_t* hist, cudaStream_t s);
 int launch_tile_histograms(const uint32_t* keys, uint64_t n, int r, int bit_group, int block, uint32_t* hist,
                            cudaStream_t s);

@@ -24,6 +24,10 @@ namespace lsd {
 // Algorithmic bytes: 4 B per key read; the 32/r * 2^r * 8 B output is negligible.
 // -------------------------------------------------------------------------------------
 constexpr int kHistThreads = 1024;
+#ifndef LSD_HIST_UNROLL
+#define LSD_HIST_UNROLL 8
+#endif
+constexpr int kHistUnroll = LSD_HIST_UNROLL;  // 128-bit loads in flight per thread
 
 template <int RB, bool TOP_ONLY = false, bool TYPED = false>
 __device__ __forceinline__ void hist_add_key(uint32_t* cnt_lane, uint32_t key, KeyXform xf = KeyXform{0u, 0u})
@@ -40,7 +44,8 @@ __device__ __forceinline__ void hist_add_key(uint32_t* cnt_lane, uint32_t key, K
 
 template <int RB, bool TOP_ONLY = false, bool TYPED = false>
 __global__ void __launch_bounds__(kHistThreads, 1)
-digit_hist_kernel(const uint32_t* __restrict__ keys, uint64_t n, unsigned long long* __restrict__ hist, KeyXform xf)
+digit_hist_kernel(const uint32_t* __restrict__ keys, uint64_t n, unsigned long long* __restrict__ hist, KeyXform xf,
+                  uint4* __restrict__ zero_ptr, uint64_t zero_vecs)
 {
     constexpr int NP = 32 / RB;
     constexpr int H = 1 << RB;
@@ -57,20 +62,20 @@ digit_hist_kernel(const uint32_t* __restrict__ keys, uint64_t n, unsigned long l
     const uint64_t stride = (uint64_t)gridDim.x * kHistThreads;
     uint64_t i = (uint64_t)blockIdx.x * kHistThreads + tid;
 
-    // main body: 4 independent 128-bit loads in flight per thread
-    for (; i + 3 * stride < nvec; i += 4 * stride) {
-        const uint4 a = ld_stream_v4(keys + 4 * i);
-        const uint4 b = ld_stream_v4(keys + 4 * (i + stride));
-        const uint4 c = ld_stream_v4(keys + 4 * (i + 2 * stride));
-        const uint4 d = ld_stream_v4(keys + 4 * (i + 3 * stride));
-        hist_add_key<RB, TOP_ONLY, TYPED>(cnt_lane, a.x, xf); hist_add_key<RB, TOP_ONLY, TYPED>(cnt_lane, a.y, xf);
-        hist_add_key<RB, TOP_ONLY, TYPED>(cnt_lane, a.z, xf); hist_add_key<RB, TOP_ONLY, TYPED>(cnt_lane, a.w, xf);
-        hist_add_key<RB, TOP_ONLY, TYPED>(cnt_lane, b.x, xf); hist_add_key<RB, TOP_ONLY, TYPED>(cnt_lane, b.y, xf);
-        hist_add_key<RB, TOP_ONLY, TYPED>(cnt_lane, b.z, xf); hist_add_key<RB, TOP_ONLY, TYPED>(cnt_lane, b.w, xf);
-        hist_add_key<RB, TOP_ONLY, TYPED>(cnt_lane, c.x, xf); hist_add_key<RB, TOP_ONLY, TYPED>(cnt_lane, c.y, xf);
-        hist_add_key<RB, TOP_ONLY, TYPED>(cnt_lane, c.z, xf); hist_add_key<RB, TOP_ONLY, TYPED>(cnt_lane, c.w, xf);
-        hist_add_key<RB, TOP_ONLY, TYPED>(cnt_lane, d.x, xf); hist_add_key<RB, TOP_ONLY, TYPED>(cnt_lane, d.y, xf);
-        hist_add_key<RB, TOP_ONLY, TYPED>(cnt_lane, d.z, xf); hist_add_key<RB, TOP_ONLY, TYPED>(cnt_lane, d.w, xf);
+    // The sort lets this kernel zero its look-back records on the side (sort.cu: sort_enqueue): the kernel is bound by
+    // its shared atomics, not by HBM, so the ~0.5 B of stores per key ride along instead of costing a memset of their own.
+    for (uint64_t z = i; z < zero_vecs; z += stride) zero_ptr[z] = make_uint4(0u, 0u, 0u, 0u);
+
+    // main body: kHistUnroll independent 128-bit loads in flight per thread
+    for (; i + (kHistUnroll - 1) * stride < nvec; i += kHistUnroll * stride) {
+        uint4 v[kHistUnroll];
+#pragma unroll
+        for (int u = 0; u < kHistUnroll; ++u) v[u] = ld_stream_v4(keys + 4 * (i + u * stride));
+#pragma unroll
+        for (int u = 0; u < kHistUnroll; ++u) {
+            hist_add_key<RB, TOP_ONLY, TYPED>(cnt_lane, v[u].x, xf); hist_add_key<RB, TOP_ONLY, TYPED>(cnt_lane, v[u].y, xf);
+            hist_add_key<RB, TOP_ONLY, TYPED>(cnt_lane, v[u].z, xf); hist_add_key<RB, TOP_ONLY, TYPED>(cnt_lane, v[u].w, xf);
+        }
     }
     for (; i < nvec; i += stride) {
         const uint4 a = ld_stream_v4(keys + 4 * i);
@@ -94,7 +99,8 @@ digit_hist_kernel(const uint32_t* __restrict__ keys, uint64_t n, unsigned long l
 }
 
 template <int RB, bool TOP_ONLY = false, bool TYPED = false>
-static int launch_digit_hist_t(const uint32_t* keys, uint64_t n, uint64_t* hist, cudaStream_t s, uint32_t key_type = 0)
+static int launch_digit_hist_t(const uint32_t* keys, uint64_t n, uint64_t* hist, cudaStream_t s, uint32_t key_type = 0,
+                               void* zero_ptr = nullptr, size_t zero_bytes = 0)
 {
     constexpr int ROWS = (32 / RB) << RB;
     const size_t smem = (size_t)ROWS * 32 * sizeof(uint32_t);
@@ -105,8 +111,10 @@ static int launch_digit_hist_t(const uint32_t* keys, uint64_t n, uint64_t* hist,
     const uint64_t slices = ((n >> 2) + kHistThreads - 1) / kHistThreads;
     int grid = sm_count();
     if ((uint64_t)grid > slices) grid = (int)(slices ? slices : 1);
+    if (zero_bytes != 0 && (!aligned_to(zero_ptr, 16) || zero_bytes % 16 != 0)) return LSD_ERR_ALIGNMENT;
     digit_hist_kernel<RB, TOP_ONLY, TYPED><<<grid, kHistThreads, smem, s>>>(keys, n, reinterpret_cast<unsigned long long*>(hist),
-                                                                            key_xform_of(key_type));
+                                                                            key_xform_of(key_type), static_cast<uint4*>(zero_ptr),
+                                                                            (uint64_t)(zero_bytes / 16));
     LSD_LAUNCH_CHECK();
     return LSD_OK;
 }
@@ -124,22 +132,23 @@ int launch_top_digit_histogram(const uint32_t* keys, uint64_t n, int r, uint64_t
     return LSD_ERR_INVALID_VALUE;
 }
 
-int launch_digit_histograms(const uint32_t* keys, uint64_t n, int r, uint64_t* hist, cudaStream_t s, uint32_t key_type)
+int launch_digit_histograms(const uint32_t* keys, uint64_t n, int r, uint64_t* hist, cudaStream_t s, uint32_t key_type, void* zero_ptr,
+                            size_t zero_bytes)
 {
     if (key_type != 0) {  // typed keys: histogram of the keys' unsigned images
         switch (r) {
-            case 1: return launch_digit_hist_t<1, false, true>(keys, n, hist, s, key_type);
-            case 2: return launch_digit_hist_t<2, false, true>(keys, n, hist, s, key_type);
-            case 4: return launch_digit_hist_t<4, false, true>(keys, n, hist, s, key_type);
-            case 8: return launch_digit_hist_t<8, false, true>(keys, n, hist, s, key_type);
+            case 1: return launch_digit_hist_t<1, false, true>(keys, n, hist, s, key_type, zero_ptr, zero_bytes);
+            case 2: return launch_digit_hist_t<2, false, true>(keys, n, hist, s, key_type, zero_ptr, zero_bytes);
+            case 4: return launch_digit_hist_t<4, false, true>(keys, n, hist, s, key_type, zero_ptr, zero_bytes);
+            case 8: return launch_digit_hist_t<8, false, true>(keys, n, hist, s, key_type, zero_ptr, zero_bytes);
         }
         return LSD_ERR_INVALID_VALUE;
     }
     switch (r) {
-        case 1: return launch_digit_hist_t<1>(keys, n, hist, s);
-        case 2: return launch_digit_hist_t<2>(keys, n, hist, s);
-        case 4: return launch_digit_hist_t<4>(keys, n, hist, s);
-        case 8: return launch_digit_hist_t<8>(keys, n, hist, s);
+        case 1: return launch_digit_hist_t<1>(keys, n, hist, s, 0, zero_ptr, zero_bytes);
+        case 2: return launch_digit_hist_t<2>(keys, n, hist, s, 0, zero_ptr, zero_bytes);
+        case 4: return launch_digit_hist_t<4>(keys, n, hist, s, 0, zero_ptr, zero_bytes);
+        case 8: return launch_digit_hist_t<8>(keys, n, hist, s, 0, zero_ptr, zero_bytes);
     }
     return LSD_ERR_INVALID_VALUE;
 }

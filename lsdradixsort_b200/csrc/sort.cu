@@ -188,8 +188,10 @@ int sort_enqueue(uint32_t* keys, uint32_t* scratch, uint64_t n, int r, int block
 
     int ev = 0, nl = 0;
     if (events) LSD_CUDA_TRY(cudaEventRecord(events[ev++], s));
-    LSD_CUDA_TRY(cudaMemsetAsync(ws, 0, L.total_bytes, s));
-    int rc = launch_digit_histograms(keys, n, r, hist, s, key_type);
+    // plan, histograms, bases and tickets are zeroed here; the look-back records (~0.5 B per key: 131 MB at 2^28 keys) by the
+    // histogram kernel, which is bound by its shared atomics and has the HBM bandwidth to spare
+    LSD_CUDA_TRY(cudaMemsetAsync(ws, 0, L.off_lookback, s));
+    int rc = launch_digit_histograms(keys, n, r, hist, s, key_type, w + L.off_lookback, L.total_bytes - L.off_lookback);
     if (rc != LSD_OK) return rc;
     ++nl;
     plan_kernel<<<1, kPlanThreads, 0, s>>>(hist, bases, plan, n, L.passes, L.H, opt ? (int)opt->disable_skip : 0);
