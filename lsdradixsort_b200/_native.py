@@ -149,6 +149,8 @@ def lib() -> C.CDLL:
         "lsd_host_ctx_create": (C.c_int, [C.c_uint64, C.c_int, C.c_int, C.POINTER(vp)]),
         "lsd_host_ctx_destroy": (C.c_int, [vp]),
         "lsd_sort_host": (C.c_int, [vp, vp, C.c_uint64]),
+        "lsd_sort_host_async": (C.c_int, [vp, vp, C.c_uint64]),
+        "lsd_host_ctx_wait": (C.c_int, [vp]),
         "lsd_host_alloc": (C.c_int, [C.POINTER(vp), C.c_size_t]),
         "lsd_host_free": (C.c_int, [vp]),
     }

@@ -399,19 +399,32 @@ class HostSorter:
         N.check(N.lib().lsd_host_ctx_create(int(max_n), r, block, C.byref(self._ctx)), "lsd_host_ctx_create")
         self.max_n = int(max_n)
 
-    def sort_(self, host_keys) -> None:
-        """``host_keys``: pinned/pageable CPU torch tensor (int32/uint32) or numpy uint32 array, sorted in place."""
+    @staticmethod
+    def _host_ptr(host_keys):
         if isinstance(host_keys, torch.Tensor):
             if host_keys.is_cuda or host_keys.dtype not in (torch.int32, torch.uint32) or not host_keys.is_contiguous():
                 raise TypeError("host_keys must be a contiguous CPU int32/uint32 tensor")
-            ptr, n = host_keys.data_ptr(), host_keys.numel()
-        else:
-            import numpy as np
+            return host_keys.data_ptr(), host_keys.numel()
+        import numpy as np
 
-            if host_keys.dtype != np.uint32 or not host_keys.flags["C_CONTIGUOUS"]:
-                raise TypeError("host_keys must be a C-contiguous uint32 array")
-            ptr, n = host_keys.ctypes.data, host_keys.size
+        if host_keys.dtype != np.uint32 or not host_keys.flags["C_CONTIGUOUS"]:
+            raise TypeError("host_keys must be a C-contiguous uint32 array")
+        return host_keys.ctypes.data, host_keys.size
+
+    def sort_(self, host_keys) -> None:
+        """``host_keys``: pinned/pageable CPU torch tensor (int32/uint32) or numpy uint32 array, sorted in place."""
+        ptr, n = self._host_ptr(host_keys)
         N.check(N.lib().lsd_sort_host(self._ctx, ptr, n), "lsd_sort_host")
+
+    def sort_async_(self, host_keys) -> None:
+        """Enqueue H2D + sort + D2H on the context's stream and return at once (``host_keys`` must be pinned and must stay
+        alive and untouched until ``wait()``).  Two HostSorters used alternately overlap the D2H copy of one array with the
+        H2D copy of the next."""
+        ptr, n = self._host_ptr(host_keys)
+        N.check(N.lib().lsd_sort_host_async(self._ctx, ptr, n), "lsd_sort_host_async")
+
+    def wait(self) -> None:
+        N.check(N.lib().lsd_host_ctx_wait(self._ctx), "lsd_host_ctx_wait")
 
     def close(self) -> None:
         if self._ctx:

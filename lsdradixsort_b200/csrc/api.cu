@@ -365,7 +365,7 @@ LSD_API int lsd_host_ctx_destroy(lsd_host_ctx* c)
     return LSD_OK;
 }
 
-LSD_API int lsd_sort_host(lsd_host_ctx* c, uint32_t* host_keys, uint64_t n)
+LSD_API int lsd_sort_host_async(lsd_host_ctx* c, uint32_t* host_keys, uint64_t n)
 {
     if (!c) return LSD_ERR_INVALID_VALUE;
     if (n > c->max_n) return LSD_ERR_INVALID_VALUE;
@@ -377,8 +377,21 @@ LSD_API int lsd_sort_host(lsd_host_ctx* c, uint32_t* host_keys, uint64_t n)
                                 nullptr, nullptr);
     if (rc != LSD_OK) return rc;
     LSD_CUDA_TRY(cudaMemcpyAsync(host_keys, c->d_keys, bytes, cudaMemcpyDeviceToHost, c->stream));
+    return LSD_OK;
+}
+
+LSD_API int lsd_host_ctx_wait(lsd_host_ctx* c)
+{
+    if (!c) return LSD_ERR_INVALID_VALUE;
     LSD_CUDA_TRY(cudaStreamSynchronize(c->stream));
     return LSD_OK;
+}
+
+LSD_API int lsd_sort_host(lsd_host_ctx* c, uint32_t* host_keys, uint64_t n)
+{
+    const int rc = lsd_sort_host_async(c, host_keys, n);
+    if (rc != LSD_OK || n == 0) return rc;
+    return lsd_host_ctx_wait(c);
 }
 
 LSD_API int lsd_host_alloc(void** ptr, size_t bytes)

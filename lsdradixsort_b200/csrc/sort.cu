@@ -3,7 +3,7 @@
 // Replaces GPULSDRadixSort (LSDRadixSort.cu:839-910).  Where the reference launches ~16 kernels
 // plus a D2D copy per pass and creates/destroys two streams per call, this enqueues, on the
 // caller's stream and without any host synchronisation:
-//     memset(workspace) -> digit_hist_kernel -> plan_kernel -> onesweep_kernel x passes -> copy_back_kernel
+//     memset(workspace header) -> digit_hist_kernel (zeroes the look-back records on the side) -> plan_kernel -> onesweep_kernel x passes -> copy_back_kernel
 // Pass skipping and ping-pong parity are decided ON THE DEVICE by plan_kernel (every pass kernel
 // reads the plan and exits at once if its digit is constant), so the sequence is fixed, fully
 // asynchronous and CUDA-graph capturable.

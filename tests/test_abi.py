@@ -107,6 +107,8 @@ def test_histogram_and_scan_argument_validation():
     assert lib.lsd_prefix_sum(0x1000, 16, 4096, 0x2000, 1 << 20, None) == N.LSD_ERR_INVALID_VALUE
     assert lib.lsd_prefix_sum(0x1004, 16, 256, 0x2000, 1 << 20, None) == N.LSD_ERR_ALIGNMENT
     assert lib.lsd_sort_host(None, None, 0) == N.LSD_ERR_INVALID_VALUE
+    assert lib.lsd_sort_host_async(None, None, 0) == N.LSD_ERR_INVALID_VALUE
+    assert lib.lsd_host_ctx_wait(None) == N.LSD_ERR_INVALID_VALUE
 
 
 def test_python_mirror_refuses_cpu_tensors():

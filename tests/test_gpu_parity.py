@@ -204,6 +204,29 @@ def test_sort_host_buffers_roundtrip():
     hs.close()
 
 
+def test_sort_host_async_two_contexts():
+    """lsd_sort_host_async / lsd_host_ctx_wait: two contexts used alternately (the D2H copy of one array overlaps the H2D copy
+    of the next); every array is compared with the oracle after its wait."""
+    n = (1 << 20) + 123
+    sorters = [L.HostSorter(n, r=8), L.HostSorter(n, r=8)]
+    bufs = [torch.empty(n, dtype=torch.int32).pin_memory() for _ in range(2)]
+    pending = [None, None]
+    for step in range(6):
+        slot = step & 1
+        if pending[slot] is not None:
+            sorters[slot].wait()
+            assert np.array_equal(bufs[slot].numpy().view(np.uint32)[: pending[slot].size], _oracle.sort(pending[slot], 8))
+        m = n - 1000 * step
+        keys = keygen.make_keys("uniform" if step % 3 else "entropy4_table", m, 40 + step)
+        bufs[slot][:m].copy_(torch.from_numpy(keys.view(np.int32)))
+        sorters[slot].sort_async_(bufs[slot][:m])
+        pending[slot] = keys
+    for slot in range(2):
+        sorters[slot].wait()
+        assert np.array_equal(bufs[slot].numpy().view(np.uint32)[: pending[slot].size], _oracle.sort(pending[slot], 8))
+        sorters[slot].close()
+
+
 def _big_uniform(n: int, seed: int) -> np.ndarray:
     """keygen.uniform_u32 in 2^26-key pieces (same values, bounded temporaries)."""
     out = np.empty(n, dtype=np.uint32)
