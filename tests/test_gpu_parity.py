@@ -149,15 +149,27 @@ def test_sort_2pow32_keys_on_one_gpu():
     assert hist_before[3][: (edge >> 24)].sum().item() <= (1 << 20)
 
 
-@pytest.mark.parametrize("r", [2, 8])
-def test_sort_multi_portion_handoff(r):
+@pytest.mark.parametrize("kind", ["entropy4_table", "uniform"])
+@pytest.mark.parametrize("r", [1, 2, 4, 8])
+def test_sort_multi_portion_handoff(r, kind):
     """Inputs above 2^30-1 keys run as several look-back portions; force tiny portions to cover the
-    bucket-base hand-off between them."""
+    bucket-base hand-off between them (r = 4 and r = 1: the quad look-back of lookback_quad.cuh writes the bases)."""
     n = 150_001
-    keys = keygen.make_keys("entropy4_table", n, seed=5)
+    keys = keygen.make_keys(kind, n, seed=5)
     d = dev(keys)
     L.sort_(d, r=r, portion_keys=16384)
     assert np.array_equal(host(d), _oracle.sort(keys, r))
+
+
+@pytest.mark.parametrize("r", [1, 4])
+def test_sort_narrow_digits_many_tiles(r):
+    """r = 4 / r = 1 at 2^24 + 77 keys (2009 tiles, ragged last tile): the quad look-back walks through deep windows."""
+    n = (1 << 24) + 77
+    g = torch.Generator(device="cuda").manual_seed(r)
+    d = torch.randint(-(2**31), 2**31, (n,), dtype=torch.int64, device="cuda", generator=g).to(torch.int32)
+    want = torch.sort(d.to(torch.int64) & 0xFFFFFFFF).values.to(torch.int32)
+    L.sort_(d, r=r)
+    assert torch.equal(d, want)
 
 
 def test_sort_reference_shaped_call_leaves_result_in_a():
