@@ -42,7 +42,10 @@ __device__ __forceinline__ void hist_add_key(uint32_t* cnt_lane, uint32_t key, K
     }
 }
 
-template <int RB, bool TOP_ONLY = false, bool TYPED = false>
+// RF < RB (narrow digits, r = 1 / 2 / 4): the keys are counted by their 8-bit digits all the same -- four shared atomics per key
+// instead of 32 / r -- and the CTA folds its 4 x 256 counts into the [32/RF][2^RF] bins before the flush (an r-bit digit is
+// a bit field of one 8-bit digit, so its histogram is a sum over that digit's bins).
+template <int RB, bool TOP_ONLY = false, bool TYPED = false, int RF = RB>
 __global__ void __launch_bounds__(kHistThreads, 1)
 digit_hist_kernel(const uint32_t* __restrict__ keys, uint64_t n, unsigned long long* __restrict__ hist, KeyXform xf,
                   uint4* __restrict__ zero_ptr, uint64_t zero_vecs)
@@ -89,32 +92,55 @@ digit_hist_kernel(const uint32_t* __restrict__ keys, uint64_t n, unsigned long l
     }
     __syncthreads();
 
-    for (uint32_t row = tid; row < ROWS; row += kHistThreads) {
-        const uint32_t* r = cnt + (row << 5);
-        uint32_t sum = 0;
+    if constexpr (RF == RB) {
+        for (uint32_t row = tid; row < ROWS; row += kHistThreads) {
+            const uint32_t* r = cnt + (row << 5);
+            uint32_t sum = 0;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) sum += r[(j + lane) & 31];
-        if (sum) atomicAdd(hist + row, (unsigned long long)sum);
+            for (int j = 0; j < 32; ++j) sum += r[(j + lane) & 31];
+            if (sum) atomicAdd(hist + row, (unsigned long long)sum);
+        }
+    } else {
+        static_assert(RB == 8 && ROWS == kHistThreads && !TOP_ONLY && RB % RF == 0, "fold: one 8-bit row per thread");
+        uint32_t sum = 0;
+        {
+            const uint32_t* r = cnt + (tid << 5);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) sum += r[(j + lane) & 31];
+        }
+        __syncthreads();  // every row has been read: its first word takes the row sum
+        cnt[tid << 5] = sum;
+        __syncthreads();
+        constexpr uint32_t HF = 1u << RF, BINS = (32u / RF) << RF;  // at most 128 bins
+        if (tid < BINS) {
+            const uint32_t digit = tid / HF, v = tid % HF;                // narrow digit `digit` = bits [digit*RF, digit*RF + RF)
+            const uint32_t row0 = (digit * RF / 8u) << 8, off = digit * RF % 8u;
+            uint32_t acc = 0;
+            for (uint32_t x = 0; x < 256u; ++x)
+                if (((x >> off) & (HF - 1u)) == v) acc += cnt[(row0 + x) << 5];
+            if (acc) atomicAdd(hist + tid, (unsigned long long)acc);
+        }
     }
 }
 
-template <int RB, bool TOP_ONLY = false, bool TYPED = false>
+template <int RB, bool TOP_ONLY = false, bool TYPED = false, int RF = RB>
 static int launch_digit_hist_t(const uint32_t* keys, uint64_t n, uint64_t* hist, cudaStream_t s, uint32_t key_type = 0,
                                void* zero_ptr = nullptr, size_t zero_bytes = 0)
 {
     constexpr int ROWS = (32 / RB) << RB;
+    constexpr int BINS = (32 / RF) << RF;
     const size_t smem = (size_t)ROWS * 32 * sizeof(uint32_t);
-    LSD_CUDA_TRY(cudaMemsetAsync(hist, 0, (size_t)ROWS * sizeof(uint64_t), s));
+    LSD_CUDA_TRY(cudaMemsetAsync(hist, 0, (size_t)BINS * sizeof(uint64_t), s));
     if (n == 0) return LSD_OK;
-    LSD_CUDA_TRY(cudaFuncSetAttribute(digit_hist_kernel<RB, TOP_ONLY, TYPED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    LSD_CUDA_TRY(cudaFuncSetAttribute(digit_hist_kernel<RB, TOP_ONLY, TYPED, RF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // one CTA per SM, but never more CTAs than there are 16 KiB slices of input
     const uint64_t slices = ((n >> 2) + kHistThreads - 1) / kHistThreads;
     int grid = sm_count();
     if ((uint64_t)grid > slices) grid = (int)(slices ? slices : 1);
     if (zero_bytes != 0 && (!aligned_to(zero_ptr, 16) || zero_bytes % 16 != 0)) return LSD_ERR_ALIGNMENT;
-    digit_hist_kernel<RB, TOP_ONLY, TYPED><<<grid, kHistThreads, smem, s>>>(keys, n, reinterpret_cast<unsigned long long*>(hist),
-                                                                            key_xform_of(key_type), static_cast<uint4*>(zero_ptr),
-                                                                            (uint64_t)(zero_bytes / 16));
+    digit_hist_kernel<RB, TOP_ONLY, TYPED, RF><<<grid, kHistThreads, smem, s>>>(keys, n, reinterpret_cast<unsigned long long*>(hist),
+                                                                                key_xform_of(key_type), static_cast<uint4*>(zero_ptr),
+                                                                                (uint64_t)(zero_bytes / 16));
     LSD_LAUNCH_CHECK();
     return LSD_OK;
 }
@@ -137,17 +163,18 @@ int launch_digit_histograms(const uint32_t* keys, uint64_t n, int r, uint64_t* h
 {
     if (key_type != 0) {  // typed keys: histogram of the keys' unsigned images
         switch (r) {
-            case 1: return launch_digit_hist_t<1, false, true>(keys, n, hist, s, key_type, zero_ptr, zero_bytes);
-            case 2: return launch_digit_hist_t<2, false, true>(keys, n, hist, s, key_type, zero_ptr, zero_bytes);
-            case 4: return launch_digit_hist_t<4, false, true>(keys, n, hist, s, key_type, zero_ptr, zero_bytes);
+            case 1: return launch_digit_hist_t<8, false, true, 1>(keys, n, hist, s, key_type, zero_ptr, zero_bytes);
+            case 2: return launch_digit_hist_t<8, false, true, 2>(keys, n, hist, s, key_type, zero_ptr, zero_bytes);
+            case 4: return launch_digit_hist_t<8, false, true, 4>(keys, n, hist, s, key_type, zero_ptr, zero_bytes);
             case 8: return launch_digit_hist_t<8, false, true>(keys, n, hist, s, key_type, zero_ptr, zero_bytes);
         }
         return LSD_ERR_INVALID_VALUE;
     }
     switch (r) {
-        case 1: return launch_digit_hist_t<1>(keys, n, hist, s, 0, zero_ptr, zero_bytes);
-        case 2: return launch_digit_hist_t<2>(keys, n, hist, s, 0, zero_ptr, zero_bytes);
-        case 4: return launch_digit_hist_t<4>(keys, n, hist, s, 0, zero_ptr, zero_bytes);
+        // narrow digits are counted as 8-bit digits (4 shared atomics per key instead of 32 / r) and folded before the flush
+        case 1: return launch_digit_hist_t<8, false, false, 1>(keys, n, hist, s, 0, zero_ptr, zero_bytes);
+        case 2: return launch_digit_hist_t<8, false, false, 2>(keys, n, hist, s, 0, zero_ptr, zero_bytes);
+        case 4: return launch_digit_hist_t<8, false, false, 4>(keys, n, hist, s, 0, zero_ptr, zero_bytes);
         case 8: return launch_digit_hist_t<8>(keys, n, hist, s, 0, zero_ptr, zero_bytes);
     }
     return LSD_ERR_INVALID_VALUE;
