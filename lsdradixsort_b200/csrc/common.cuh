@@ -129,6 +129,7 @@ int smem_optin_bytes();  // cached max opt-in shared memory per block
 int launch_digit_histograms(const uint32_t* keys, uint64_t n, int r, uint64_t* hist, cudaStream_t s,
                             uint32_t key_type = 0, void* zero_ptr = nullptr, size_t zero_bytes = 0);
 int launch_top_digit_histogram(const uint32_t* keys, uint64_t n, int r, uint64_t* hist, cudaStream_t s);
+int launch_one_digit_histogram(const uint32_t* keys, uint64_t n, int r, int digit, uint64_t* hist, cudaStream_t s);
 int launch_tile_histograms(const uint32_t* keys, uint64_t n, int r, int bit_group, int block, uint32_t* hist,
                            cudaStream_t s);
 int launch_field_histogram(const uint32_t* keys, uint64_t n, int shift, int bits, uint64_t* hist, cudaStream_t s);

@@ -29,16 +29,22 @@ constexpr int kHistThreads = 1024;
 #endif
 constexpr int kHistUnroll = LSD_HIST_UNROLL;  // 128-bit loads in flight per thread
 
+// TOP_ONLY: ONE digit only (run-time index `one`: the top digit for the multi-GPU planning step, any digit for lsd_sort_pass)
 template <int RB, bool TOP_ONLY = false, bool TYPED = false>
-__device__ __forceinline__ void hist_add_key(uint32_t* cnt_lane, uint32_t key, KeyXform xf = KeyXform{0u, 0u})
+__device__ __forceinline__ void hist_add_key(uint32_t* cnt_lane, uint32_t key, KeyXform xf = KeyXform{0u, 0u}, uint32_t one = 0)
 {
     constexpr int NP = 32 / RB;
     constexpr int H = 1 << RB;
     if constexpr (TYPED) key = key_to_unsigned(key, xf);
+    if constexpr (TOP_ONLY) {
+        const uint32_t d = (key >> (one * RB)) & (H - 1);
+        atomicAdd(cnt_lane + ((one * H + d) << 5), 1u);
+    } else {
 #pragma unroll
-    for (int p = TOP_ONLY ? NP - 1 : 0; p < NP; ++p) {
-        const uint32_t d = (key >> (p * RB)) & (H - 1);
-        atomicAdd(cnt_lane + ((p * H + d) << 5), 1u);
+        for (int p = 0; p < NP; ++p) {
+            const uint32_t d = (key >> (p * RB)) & (H - 1);
+            atomicAdd(cnt_lane + ((p * H + d) << 5), 1u);
+        }
     }
 }
 
@@ -48,7 +54,7 @@ __device__ __forceinline__ void hist_add_key(uint32_t* cnt_lane, uint32_t key, K
 template <int RB, bool TOP_ONLY = false, bool TYPED = false, int RF = RB>
 __global__ void __launch_bounds__(kHistThreads, 1)
 digit_hist_kernel(const uint32_t* __restrict__ keys, uint64_t n, unsigned long long* __restrict__ hist, KeyXform xf,
-                  uint4* __restrict__ zero_ptr, uint64_t zero_vecs)
+                  uint4* __restrict__ zero_ptr, uint64_t zero_vecs, uint32_t one)
 {
     constexpr int NP = 32 / RB;
     constexpr int H = 1 << RB;
@@ -76,19 +82,19 @@ digit_hist_kernel(const uint32_t* __restrict__ keys, uint64_t n, unsigned long l
         for (int u = 0; u < kHistUnroll; ++u) v[u] = ld_stream_v4(keys + 4 * (i + u * stride));
 #pragma unroll
         for (int u = 0; u < kHistUnroll; ++u) {
-            hist_add_key<RB, TOP_ONLY, TYPED>(cnt_lane, v[u].x, xf); hist_add_key<RB, TOP_ONLY, TYPED>(cnt_lane, v[u].y, xf);
-            hist_add_key<RB, TOP_ONLY, TYPED>(cnt_lane, v[u].z, xf); hist_add_key<RB, TOP_ONLY, TYPED>(cnt_lane, v[u].w, xf);
+            hist_add_key<RB, TOP_ONLY, TYPED>(cnt_lane, v[u].x, xf, one); hist_add_key<RB, TOP_ONLY, TYPED>(cnt_lane, v[u].y, xf, one);
+            hist_add_key<RB, TOP_ONLY, TYPED>(cnt_lane, v[u].z, xf, one); hist_add_key<RB, TOP_ONLY, TYPED>(cnt_lane, v[u].w, xf, one);
         }
     }
     for (; i < nvec; i += stride) {
         const uint4 a = ld_stream_v4(keys + 4 * i);
-        hist_add_key<RB, TOP_ONLY, TYPED>(cnt_lane, a.x, xf); hist_add_key<RB, TOP_ONLY, TYPED>(cnt_lane, a.y, xf);
-        hist_add_key<RB, TOP_ONLY, TYPED>(cnt_lane, a.z, xf); hist_add_key<RB, TOP_ONLY, TYPED>(cnt_lane, a.w, xf);
+        hist_add_key<RB, TOP_ONLY, TYPED>(cnt_lane, a.x, xf, one); hist_add_key<RB, TOP_ONLY, TYPED>(cnt_lane, a.y, xf, one);
+        hist_add_key<RB, TOP_ONLY, TYPED>(cnt_lane, a.z, xf, one); hist_add_key<RB, TOP_ONLY, TYPED>(cnt_lane, a.w, xf, one);
     }
     // ragged tail (n % 4 keys) -- block 0 only
     if (blockIdx.x == 0) {
         const uint64_t t = (nvec << 2) + tid;
-        if (t < n) hist_add_key<RB, TOP_ONLY, TYPED>(cnt_lane, keys[t], xf);
+        if (t < n) hist_add_key<RB, TOP_ONLY, TYPED>(cnt_lane, keys[t], xf, one);
     }
     __syncthreads();
 
@@ -125,7 +131,7 @@ digit_hist_kernel(const uint32_t* __restrict__ keys, uint64_t n, unsigned long l
 
 template <int RB, bool TOP_ONLY = false, bool TYPED = false, int RF = RB>
 static int launch_digit_hist_t(const uint32_t* keys, uint64_t n, uint64_t* hist, cudaStream_t s, uint32_t key_type = 0,
-                               void* zero_ptr = nullptr, size_t zero_bytes = 0)
+                               void* zero_ptr = nullptr, size_t zero_bytes = 0, uint32_t one = 32 / RB - 1)
 {
     constexpr int ROWS = (32 / RB) << RB;
     constexpr int BINS = (32 / RF) << RF;
@@ -140,22 +146,29 @@ static int launch_digit_hist_t(const uint32_t* keys, uint64_t n, uint64_t* hist,
     if (zero_bytes != 0 && (!aligned_to(zero_ptr, 16) || zero_bytes % 16 != 0)) return LSD_ERR_ALIGNMENT;
     digit_hist_kernel<RB, TOP_ONLY, TYPED, RF><<<grid, kHistThreads, smem, s>>>(keys, n, reinterpret_cast<unsigned long long*>(hist),
                                                                                 key_xform_of(key_type), static_cast<uint4*>(zero_ptr),
-                                                                                (uint64_t)(zero_bytes / 16));
+                                                                                (uint64_t)(zero_bytes / 16), one);
     LSD_LAUNCH_CHECK();
     return LSD_OK;
 }
 
-// Top digit only (one shared atomic per key instead of 32/r): the multi-GPU planning step.  Same [32/r][2^r] layout,
-// the other rows are zero.
-int launch_top_digit_histogram(const uint32_t* keys, uint64_t n, int r, uint64_t* hist, cudaStream_t s)
+// One digit only (one shared atomic per key instead of 32/r): the top digit for the multi-GPU planning step, the digit of the
+// pass for lsd_sort_pass.  Same [32/r][2^r] layout, the other rows are zero.
+int launch_one_digit_histogram(const uint32_t* keys, uint64_t n, int r, int digit, uint64_t* hist, cudaStream_t s)
 {
+    if (digit < 0 || digit >= 32 / r) return LSD_ERR_INVALID_VALUE;
     switch (r) {
-        case 1: return launch_digit_hist_t<1, true>(keys, n, hist, s);
-        case 2: return launch_digit_hist_t<2, true>(keys, n, hist, s);
-        case 4: return launch_digit_hist_t<4, true>(keys, n, hist, s);
-        case 8: return launch_digit_hist_t<8, true>(keys, n, hist, s);
+        case 1: return launch_digit_hist_t<1, true>(keys, n, hist, s, 0, nullptr, 0, (uint32_t)digit);
+        case 2: return launch_digit_hist_t<2, true>(keys, n, hist, s, 0, nullptr, 0, (uint32_t)digit);
+        case 4: return launch_digit_hist_t<4, true>(keys, n, hist, s, 0, nullptr, 0, (uint32_t)digit);
+        case 8: return launch_digit_hist_t<8, true>(keys, n, hist, s, 0, nullptr, 0, (uint32_t)digit);
     }
     return LSD_ERR_INVALID_VALUE;
+}
+
+int launch_top_digit_histogram(const uint32_t* keys, uint64_t n, int r, uint64_t* hist, cudaStream_t s)
+{
+    if (r != 1 && r != 2 && r != 4 && r != 8) return LSD_ERR_INVALID_VALUE;
+    return launch_one_digit_histogram(keys, n, r, 32 / r - 1, hist, s);
 }
 
 int launch_digit_histograms(const uint32_t* keys, uint64_t n, int r, uint64_t* hist, cudaStream_t s, uint32_t key_type, void* zero_ptr,

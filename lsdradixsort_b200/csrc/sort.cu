@@ -310,7 +310,7 @@ int pass_enqueue(const uint32_t* in, uint32_t* out, uint64_t n, int r, int bit_g
     LSD_CUDA_TRY(cudaMemsetAsync(ws, 0, L.off_lookback + sizeof(uint32_t) * lb_words_per_pass, s));
     int rc = LSD_OK;
     if (!peer) {  // peer-scatter offsets start at 0 in every destination: no global histogram needed
-        rc = launch_digit_histograms(in, n, r, hist, s);
+        rc = launch_one_digit_histogram(in, n, r, bit_group, hist, s);  // the digit of this pass only: one shared atomic per key
         if (rc != LSD_OK) return rc;
     }
     single_pass_plan_kernel<<<1, kPlanThreads, 0, s>>>(hist, bases, plan, peer ? nullptr : hist_out, bit_group, L.H, peer ? 1 : 0, abort_flag);
