@@ -39,6 +39,8 @@ __device__ __forceinline__ void tma_bulk_wait_read_all()
 // CLR: 8 = as 0, and the look-back records are PUBLISHED by TMA bulk stores from a shared-memory copy of the record (they
 //      do not queue behind the copy-out stores of the three resident CTAs in the LSU pipe)
 // CLR: 0 = matrix cleared with 128-bit stores, 1 = st.bulk, 2 = TMA copy of a zero page (keeps the clear off the LSU pipe)
+// CLR: 9 = as 0 with the pipelined look-back walk; 10 = as 0 with the quad look-back of lookback_quad.cuh (LB load instructions
+//      per round, each fetching 32 / (quads per look-back warp) records: the default of r = 4 and r = 1)
 // NOB5: 1 = no CTA-wide barrier at the end of a tile: the next ticket is handed over through a second mbarrier
 // TYPED: i32 / f32 keys are mapped to unsigned order when the first executed pass reads them and back when the last one writes
 // TRACE: per-tile phase clocks into PassArgs.trace (bench_tools/trace.py).  Compile-time: the run-time checks and the clock
